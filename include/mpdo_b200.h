@@ -1,0 +1,124 @@
+/*
+ * mpdo_b200.h — C ABI of libmpdo_b200.so: the B200 (sm_100a) kernels behind the
+ * MPDOSimulator noisy-gate update path.
+ *
+ * The reference (WeiguoMa/Tomography-assisted-MPDO-QCircuit) is pure Python; the only
+ * seam it exposes for this path is the TensorNetwork-pytorch backend it asks users to
+ * overwrite (README.md:17):
+ *     decompositions.svd(torch, tensor, pivot_axis, max_singular_values,
+ *                        max_truncation_error, relative)      decompositions.py:51-146
+ *     decompositions.qr (torch, tensor, pivot_axis, ...)      decompositions.py:149-195
+ * plus the tensornetwork 0.4.6 contraction calls reached from Circuit.py / TNNOptimizer.py
+ * (tn.contract, tn.contract_between, tn.contractors.optimal/auto -> torch.tensordot).
+ * Each entry point below names the reference call site(s) it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and no entry
+ *     point synchronises unless documented ("SYNC");
+ *   - complex data are interleaved (re, im); dtype 0 = complex64, 1 = complex128;
+ *   - tensors are row-major; every entry point carries a leading batch dimension (independent
+ *     circuits / brick pairs);
+ *   - return value: 0 on success, a negative MPDO_E* code on argument errors, or the positive
+ *     cudaError_t of the failing runtime call. mpdo_last_error() gives a message.
+ */
+#ifndef MPDO_B200_H_
+#define MPDO_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPDO_C64 0
+#define MPDO_C128 1
+
+#define MPDO_EINVAL (-1)  /* bad argument */
+#define MPDO_ENOSMEM (-2) /* problem does not fit the kernel's shared-memory tiling */
+
+/* Composite index: a logical index i in [0, prod) addresses
+ *   (i % d0) * s0 + ((i / d0) % d1) * s1 + (i / (d0*d1)) * s2     (elements, not bytes)
+ * d0 <= 0 means single level (i * s0); d1 <= 0 means two levels. This is how one kernel
+ * serves every axis grouping of T[l,s,a,r] without a transpose pass. */
+typedef struct {
+  int32_t d0, d1;
+  int64_t s0, s1, s2;
+} mpdo_idxmap;
+
+/* Batched complex contraction  C[b,i,j] = alpha * sum_k opA(A[b,i,k]) * opB(B[b,k,j]) + beta * C[b,i,j]
+ * with op = identity or complex conjugate, and every logical axis (b, i, j, k) a composite
+ * index over up to three tensor axes of the operand.
+ * Replaces: tn.contract / tn.contract_between / tn.contractors.optimal (torch.tensordot) at
+ *   Circuit.py:104,171 (gate absorption), TNNOptimizer.py:105 (R absorbed into the right
+ *   neighbour), :126 (two-site bond merge), :191 (U*S), and the `@` products inside
+ *   decompositions.py:39,43,46. */
+typedef struct {
+  int32_t M, N, K, batch;
+  int32_t dtypeA, dtypeB, dtypeC; /* MPDO_C64 / MPDO_C128 */
+  int32_t conjA, conjB;
+  int32_t acc64;                  /* 1: accumulate in fp64 (always when any operand is c128) */
+  int32_t a_kfast, b_jfast;       /* loader hints: which axis of A / B is contiguous */
+  int32_t ksplit;                 /* >1: split K over CTAs, atomically accumulated (C must be pre-zeroed or beta==1) */
+  double alpha, beta;
+  mpdo_idxmap Ab, Ai, Ak;
+  mpdo_idxmap Bb, Bk, Bj;
+  mpdo_idxmap Cb, Ci, Cj;
+} mpdo_contract_desc;
+
+int mpdo_contract(const mpdo_contract_desc* d, const void* A, const void* B, void* C, void* stream);
+
+/* Single-qubit gate / Kraus absorption into a site tensor (inner index grows by K, new index major):
+ *   Tout[b,l,p,(g,a),r] = sum_s G[b?,p,s,g] * T[b,l,s,a,r]
+ * G is [2,2,K] row-major per batch entry (gBatchStride = 0 shares one gate across the batch).
+ * Replaces: Circuit.py:138-178 (_apply_single_qubit_gate: tn.contract + tn.flatten_edges). */
+int mpdo_absorb_1q(int dtype, int batch, int l, int a, int r, int K, const void* T, const void* G,
+                   int64_t gBatchStride, void* Tout, void* stream);
+
+/* One-sided (Hestenes) Jacobi on the rows of Y[b] (n rows, leading dimension ld, complex128):
+ * rows are mixed by a unitary J until the first m entries of every pair of rows are orthogonal;
+ * the mixing is applied to all mt >= m entries (entries m..mt-1 carry an accumulator, e.g. the
+ * identity, which ends up holding J). In place. `work` must hold batch*48 int32, 8-byte aligned (scratch).
+ * Converges when every |<y_p,y_q>| <= tol*|y_p||y_q|, at most maxSweeps (<= 32) sweeps.
+ * Replaces: torch.linalg.svd (LAPACK gesdd) at decompositions.py:45,113 for the small cores. */
+int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t batchStride, void* Y, double tol,
+                     int maxSweeps, int32_t* work, void* stream);
+
+/* After mpdo_jacobi_rows: row norms (over the first m entries) sorted descending into s[b,n], and
+ * optionally the sorted rows themselves:
+ *   Yn[b,j,0..m)  = row / norm  if normalize (0 where norm <= zeroTol * maxnorm), else row      (may be NULL)
+ *   Z [b,j,0..mz) = entries m..m+mz of the row (the accumulator)                                  (may be NULL)
+ * Yn and Z are complex128, dense row-major. */
+int mpdo_rows_finalize(int batch, int n, int m, int mz, int ld, int64_t batchStride, const void* Y, double* s,
+                       void* Yn, void* Z, int normalize, double zeroTol, void* stream);
+
+/* X[b,j,c] = f(lam[b,j]) * V[b,j,c] for j < rows, c < cols, with f(x) = x^power and
+ *   mode 0: f = 0 where lam[b,j] <= tol*lam[b,0]      (drop numerically null directions)
+ *   mode 1: lam clamped from below at tol*lam[b,0]    (floor, for the first pass of a two-pass orthogonalisation)
+ * V is complex128 [b, vRows, cols] (first `rows` rows used); X has dtype `dtypeX`. */
+int mpdo_rowscale(int batch, int rows, int cols, int vRows, const void* V, const double* lam, int lamStride,
+                  double power, double tol, int mode, int dtypeX, void* X, void* stream);
+
+/* The reference's kept-rank rule (decompositions.py:117-134) evaluated on device for sorted
+ * singular values s[b,0..n) (or their squares when squared = 1, as produced by a Gram eigen-solve):
+ * keep[b] = min(cap, first idx+1 with ||s|| - ||s[:idx+1]|| <= eps), eps = maxTruncErr * s[0] if
+ * relative. f32 = 1 reproduces the complex64 arithmetic (fp32 values, cumsum rounded to fp32 per
+ * element). maxTruncErr < 0 means "None". zeroTail = 1 zeroes s[b, keep[b]..n) in place so that a
+ * batch padded to a common rank carries exact zeros in the discarded directions. */
+int mpdo_rank_rule(int batch, int n, double* s, int sStride, int squared, int cap, double maxTruncErr,
+                   int relative, int f32, int32_t* keep, int zeroTail, void* stream);
+
+/* Elementwise dtype conversion between complex64 and complex128 (count complex elements). */
+int mpdo_cast(int dtypeIn, int dtypeOut, int64_t count, const void* in, void* out, void* stream);
+
+/* Library / device information. */
+int mpdo_version(void);
+const char* mpdo_last_error(void);
+int mpdo_device_info(int* smCount, int* smemPerBlockOptin, int* ccMajor, int* ccMinor);
+/* Number of kernels launched by this library since load (bench.py's gpu_launches). */
+int64_t mpdo_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPDO_B200_H_ */

@@ -1,0 +1,23 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, 'tomography-assisted-mpdo-qcircuit_b200')
+for p in (ROOT, PKG, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+@pytest.fixture(scope='session')
+def cuda_prims():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from MPDOSimulator._engine.prims import CudaPrims
+    return CudaPrims()

@@ -1,0 +1,409 @@
+"""The MPDO noisy-gate update path expressed over the device primitives (prims.py).
+
+State: one dense site tensor T_k[B, l, s, a, r] per qubit (B independent circuits, bond l / r,
+physical s = 2, inner "Kraus" index a). Everything the reference does through tensornetwork
+(Circuit.py:74-224, TNNOptimizer.py:72-197) becomes a short sequence of batched contractions,
+Gram matrices and small fp64 Jacobi decompositions:
+
+* every tall/wide factor is orthogonalised through its Gram matrix (fp64) and a Jacobi
+  eigen-decomposition of that small matrix ("Gram-eig"); one pass is exact to ~1e-8 relative, which
+  is below complex64 resolution; complex128 states run two passes (the second on the already
+  nearly-orthonormal factor), which restores fp64 backward stability, followed by a one-sided Jacobi
+  SVD of the small core;
+* the right-to-left chi sweep never forms the reference's (l*s*a)^2 two-site matrix: the left
+  neighbour is an isometry after the QR sweep, so SVD(Q*X) = Q*SVD(X);
+* the two-qubit gate split factors both sites first and decomposes only the (2x) x (2Ky) core.
+
+Singular-vector gauges are not unique; all comparisons with the reference use gauge-invariant
+quantities. The inner index order is (new Kraus index major, old index minor) - a pure relabelling of
+an index that is only ever traced against its own conjugate.
+"""
+import torch
+
+C128 = torch.complex128
+
+
+class Engine:
+    def __init__(self, prims, dtype, npass=None):
+        self.p = prims
+        self.dtype = dtype
+        self.f32 = dtype == torch.complex64
+        self.npass = npass if npass is not None else (1 if self.f32 else 2)
+        self.null_tol = 1e-14    # relative eigenvalue below which a Gram direction is treated as null
+        self.floor_tol = 1e-13   # first-pass floor of the two-pass scheme
+        self.jacobi_tol = 1e-15
+        self.stats = {'discarded': []}
+
+    # ------------------------------------------------------------------------------------------
+    # helpers
+    # ------------------------------------------------------------------------------------------
+    def _empty(self, shape, like, dtype=None):
+        return torch.empty(shape, dtype=dtype or self.dtype, device=like.device)
+
+    def _gram_cols(self, X, roles):
+        """G[b,c,c'] = sum_rows conj(X[b,rows,c]) X[b,rows,c'] for a view X [b | rows | cols]."""
+        nb, nr, nc = roles
+        dims = list(range(X.dim()))
+        At = X.permute(dims[:nb] + dims[nb + nr:] + dims[nb:nb + nr])
+        n = 1
+        for d in X.shape[nb + nr:]:
+            n *= d
+        Bn = 1
+        for d in X.shape[:nb]:
+            Bn *= d
+        G = self._empty((Bn, n, n), X, C128)
+        self.p.contract(At, (nb, nc, nr), X, (nb, nr, nc), G, (1, 1, 1), conjA=True, acc64=True)
+        return G
+
+    def _gram_rows(self, M, roles):
+        """G[b,i,i'] = sum_cols M[b,i,cols] conj(M[b,i',cols]) for a view M [b | rows | cols]."""
+        nb, nr, nc = roles
+        dims = list(range(M.dim()))
+        Mt = M.permute(dims[:nb] + dims[nb + nr:] + dims[nb:nb + nr])
+        n = 1
+        for d in M.shape[nb:nb + nr]:
+            n *= d
+        Bn = 1
+        for d in M.shape[:nb]:
+            Bn *= d
+        G = self._empty((Bn, n, n), M, C128)
+        self.p.contract(M, (nb, nr, nc), Mt, (nb, nc, nr), G, (1, 1, 1), conjB=True, acc64=True)
+        return G
+
+    def orth_cols(self, X, roles):
+        """Tall view X [b | rows | cols] -> (Alast, Xs, R): Q = Alast . Xs^h is an isometry (zero columns
+        for numerically null directions) and X = Q . R. Xs, R are [B, n, n] complex128."""
+        p = self.p
+        nb, nr, nc = roles
+        G = self._gram_cols(X, roles)
+        lam, Vh = p.eigh_psd(G, self.jacobi_tol)
+        n = G.shape[1]
+        if self.npass == 1:
+            Xs = p.rowscale(Vh, lam, n, -0.5, self.null_tol, 0, C128)
+            R = p.rowscale(Vh, lam, n, 0.5, self.null_tol, 0, C128)
+            return X, Xs, R
+        Xs1 = p.rowscale(Vh, lam, n, -0.5, self.floor_tol, 1, C128)
+        R1 = p.rowscale(Vh, lam, n, 0.5, self.floor_tol, 1, C128)
+        A1 = self._empty(tuple(X.shape), X)                      # same logical shape as the view X
+        p.contract(X, roles, Xs1.permute(0, 2, 1), (1, 1, 1), A1, roles, conjB=True)
+        G2 = self._gram_cols(A1, roles)
+        lam2, Vh2 = p.eigh_psd(G2, self.jacobi_tol)
+        Xs2 = p.rowscale(Vh2, lam2, n, -0.5, self.null_tol, 0, C128)
+        R2 = p.rowscale(Vh2, lam2, n, 0.5, self.null_tol, 0, C128)
+        R = self._empty(R1.shape, X, C128)
+        p.contract(R2, (1, 1, 1), R1, (1, 1, 1), R, (1, 1, 1))
+        return A1, Xs2, R
+
+    def orth_rows(self, M, roles):
+        """Wide view M [b | rows | cols] -> (Mlast, F, Lh): Qt = F . Mlast has orthonormal (or zero) rows and
+        M = Lh^h . Qt. F, Lh are [B, l, l] complex128."""
+        p = self.p
+        nb, nr, nc = roles
+        G = self._gram_rows(M, roles)
+        lam, Uh = p.eigh_psd(G, self.jacobi_tol)
+        n = G.shape[1]
+        if self.npass == 1:
+            F = p.rowscale(Uh, lam, n, -0.5, self.null_tol, 0, C128)
+            Lh = p.rowscale(Uh, lam, n, 0.5, self.null_tol, 0, C128)
+            return M, F, Lh
+        F1 = p.rowscale(Uh, lam, n, -0.5, self.floor_tol, 1, C128)
+        R1 = p.rowscale(Uh, lam, n, 0.5, self.floor_tol, 1, C128)
+        M1 = self._empty(tuple(M.shape), M)                      # same logical shape as the view M
+        p.contract(F1, (1, 1, 1), M, roles, M1, roles)
+        G2 = self._gram_rows(M1, roles)
+        lam2, Uh2 = p.eigh_psd(G2, self.jacobi_tol)
+        F2 = p.rowscale(Uh2, lam2, n, -0.5, self.null_tol, 0, C128)
+        R2 = p.rowscale(Uh2, lam2, n, 0.5, self.null_tol, 0, C128)
+        Lh = self._empty(R1.shape, M, C128)
+        p.contract(R2, (1, 1, 1), R1, (1, 1, 1), Lh, (1, 1, 1))
+        return M1, F2, Lh
+
+    def _svd_core(self, Lh):
+        """L = Lh^h = U diag(s) Wh. Returns (Uh_L [B,n,n], s [B,n], Wh_L [B,n,n]) with rows sorted by s."""
+        Uh_, s, Wh_ = self.p.svd_rows(Lh, self.jacobi_tol)
+        return Wh_, s, Uh_
+
+    def _keep(self, s, cap, max_err, relative, squared=False):
+        """Apply the reference rank rule; returns the common (batch-max) kept rank. s is zero-tailed in place."""
+        n = s.shape[1]
+        cap = n if cap is None else min(int(cap), n)
+        if max_err is None:
+            return cap
+        keep = self.p.rank_rule(s, squared, cap, max_err, relative, self.f32, True)
+        return max(1, max(keep))
+
+    # ------------------------------------------------------------------------------------------
+    # R1: single-qubit gate / Kraus absorption          Circuit.py:138-178
+    # ------------------------------------------------------------------------------------------
+    def absorb_1q(self, T, G):
+        """T [B,l,2,a,r], G [Bg,2,2,K] -> [B,l,2,K*a,r]."""
+        return self.p.absorb_1q(T.contiguous(), G.contiguous())
+
+    # ------------------------------------------------------------------------------------------
+    # R2: two-qubit gate absorption and split           Circuit.py:74-136
+    # ------------------------------------------------------------------------------------------
+    def split_2q(self, Tlo, Thi, G, max_err=2.718281828459045e-8):
+        """Tlo [B,l,2,a0,m], Thi [B,m,2,a1,r], G [Bg,2,2,2,2,K] as [p_lo,p_hi,s_lo,s_hi,g].
+        Returns (Tlo' [B,l,2,a0,k], Thi' [B,k,2,K*a1,r]) = (U sqrt(S), sqrt(S) Vh) of the merged two-site
+        tensor, rank chosen by the reference rule ||s|| - ||s[:k]|| <= max_err (absolute)."""
+        p = self.p
+        Bn, l, _, a0, m = Tlo.shape
+        _, _, _, a1, r = Thi.shape
+        K = G.shape[-1]
+        dev = Tlo.device
+
+        # left factor: rows (l,a0), cols (s0,m)
+        Xlo = Tlo.permute(0, 1, 3, 2, 4)                        # [B,l,a0,2,m]
+        if l * a0 > 2 * m:
+            Alo, Xs_lo, Rp = self.orth_cols(Xlo, (1, 2, 2))     # Q' = Alo . Xs_lo^h ; Rp [B,x,(s0,m)]
+            x = 2 * m
+        else:
+            x = l * a0
+            Alo, Xs_lo = None, None
+            Rp = Xlo.reshape(Bn, x, 2 * m).to(C128)
+        # right factor: rows (m,s1), cols (a1,r)
+        if a1 * r > 2 * m:
+            Mhi, F_hi, Lh_hi = self.orth_rows(Thi, (1, 2, 2))   # Qt' = F_hi . Mhi ; Thi = Lh_hi^h . Qt'
+            y = 2 * m
+        else:
+            y = a1 * r
+            Mhi, F_hi = None, None
+            Lh_hi = None
+        # D[b,x,s0,s1,y] = sum_m R'[x,s0,m] L'[m,s1,y]
+        D = torch.empty((Bn, x, 2, 2, y), dtype=C128, device=dev)
+        Rp5 = Rp.reshape(Bn, x, 2, 1, m).expand(Bn, x, 2, 2, m).permute(0, 2, 3, 1, 4)     # [b,s0,s1 | x | m]
+        if Lh_hi is not None:
+            # L'[(m,s1),y] = conj(Lh_hi[y,(m,s1)])
+            Lv = Lh_hi.reshape(Bn, y, m, 1, 2).expand(Bn, y, m, 2, 2).permute(0, 3, 4, 2, 1)  # [b,s0,s1 | m | y]
+            p.contract(Rp5, (3, 1, 1), Lv, (3, 1, 1), D.permute(0, 2, 3, 1, 4), (3, 1, 1), conjB=True)
+        else:
+            Lv = Thi.reshape(Bn, m, 1, 2, y).expand(Bn, m, 2, 2, y).permute(0, 2, 3, 1, 4)    # [b,s0,s1 | m | y]
+            p.contract(Rp5, (3, 1, 1), Lv, (3, 1, 1), D.permute(0, 2, 3, 1, 4), (3, 1, 1))
+        # Cm[b,x,p0,p1,g,y] = sum_{s0,s1} G[p0,p1,s0,s1,g] D[b,x,s0,s1,y]
+        Gp = G.permute(0, 1, 2, 5, 3, 4).contiguous().to(C128)                               # [Bg,p0,p1,g,s0,s1]
+        Cm = torch.empty((Bn, x, 2, 2, K, y), dtype=C128, device=dev)
+        GpE = Gp.reshape(Gp.shape[0], 1, 4 * K, 4).expand(Bn, x, 4 * K, 4)
+        p.contract(GpE, (2, 1, 1), D.reshape(Bn, x, 4, y), (2, 1, 1), Cm.reshape(Bn, x, 4 * K, y), (2, 1, 1))
+        # SVD of the core as rows (x,p0) x cols (p1,g,y)
+        Cv = Cm.reshape(Bn, 2 * x, 2 * K * y)
+        nrow, ncol = 2 * x, 2 * K * y
+        if nrow <= ncol:
+            Mlast, F, Lh = self.orth_rows(Cv, (1, 1, 1))
+            Uh_L, s, Wh_L = self._svd_core(Lh)                   # core = U_L diag(s) Wh_L . (F . Mlast)
+            k = self._keep(s, None, max_err, False)
+            # Tlo'[(x,p0), j] = U_L[(x,p0), j] sqrt(s_j) -> conj of rowscale(Uh_L)
+            UL = p.rowscale(Uh_L, s, k, 0.5, 0.0, 0, C128)       # [B,k,(x,p0)], entries sqrt(s_j) conj(U)[.,j]
+            WF = torch.empty((Bn, k, nrow), dtype=C128, device=dev)
+            p.contract(p.rowscale(Wh_L, s, k, 0.5, 0.0, 0, C128), (1, 1, 1), F, (1, 1, 1), WF, (1, 1, 1))
+            Zc = torch.empty((Bn, k, 2, K, y), dtype=C128 if F_hi is not None else self.dtype, device=dev)
+            p.contract(WF, (1, 1, 1), Mlast, (1, 1, 1), Zc.reshape(Bn, k, ncol), (1, 1, 1))
+        else:
+            # tall core (rare: tiny right factor): decompose the column side instead
+            Alast, Xs, R = self.orth_cols(Cv, (1, 1, 1))         # Cv = (Alast Xs^h) R, R [B,ncol,ncol]
+            Uh_, s, Wh_ = p.svd_rows(R, self.jacobi_tol)          # R = Uh_^h diag(s) Wh_
+            k = self._keep(s, None, max_err, False)
+            # U_L = Q . Uh_^h  ->  UL rows: sqrt(s_j) conj(U_L[:, j])
+            XU = torch.empty((Bn, k, ncol), dtype=C128, device=dev)
+            p.contract(p.rowscale(Uh_, s, k, 0.5, 0.0, 0, C128), (1, 1, 1), Xs.permute(0, 2, 1), (1, 1, 1), XU,
+                       (1, 1, 1), conjB=True)                     # sqrt(s) Uh_ Xs^*... see note below
+            UL = torch.empty((Bn, k, nrow), dtype=C128, device=dev)
+            p.contract(XU, (1, 1, 1), Alast.permute(0, 2, 1), (1, 1, 1), UL, (1, 1, 1), conjB=True)
+            Zc = p.rowscale(Wh_, s, k, 0.5, 0.0, 0, C128 if F_hi is not None else self.dtype).reshape(Bn, k, 2, K, y)
+        self.stats['last_rank'] = k
+
+        # Tlo'[b,l,p0,a0,j] = sum_x Q'[(l,a0),x] conj(UL[j,(x,p0)])
+        Tlo_n = self._empty((Bn, l, 2, a0, k), Tlo)
+        ULv = UL.reshape(Bn, k, x, 2)
+        if Alo is not None:
+            # W[b,c,(p0,j)] = sum_x conj(Xs_lo[x,c]) conj(UL[j,x,p0]);   Tlo' = Alo . W
+            W = torch.empty((Bn, 2 * m, 2, k), dtype=self.dtype, device=dev)
+            p.contract(Xs_lo.permute(0, 2, 1), (1, 1, 1), ULv.permute(0, 2, 3, 1), (1, 1, 2), W.reshape(Bn, 2 * m, 2 * k),
+                       (1, 1, 1), conjA=True, conjB=True)
+            p.contract(Alo, (1, 2, 2), W.reshape(Bn, 2, m, 2, k), (1, 2, 2), Tlo_n.permute(0, 1, 3, 2, 4), (1, 2, 2))
+        else:
+            Tlo_n.copy_(ULv.reshape(Bn, k, l, a0, 2).permute(0, 2, 4, 3, 1).conj())
+        # Thi'[b,j,p1,(g,a1),r] = sum_y Zc[j,p1,g,y] Qt'[y,(a1,r)]
+        if F_hi is not None:
+            # Zc . F_hi -> [B,k,2,K,(m,s1)] then times Mhi [b | m,s1 | a1,r]
+            ZF = torch.empty((Bn, k * 2 * K, 2 * m), dtype=self.dtype, device=dev)
+            p.contract(Zc.reshape(Bn, k * 2 * K, y), (1, 1, 1), F_hi, (1, 1, 1), ZF, (1, 1, 1))
+            Thi_n = self._empty((Bn, k, 2, K * a1, r), Thi)
+            p.contract(ZF.reshape(Bn, k * 2 * K, m, 2), (1, 1, 2), Mhi, (1, 2, 2),
+                       Thi_n.reshape(Bn, k * 2 * K, a1, r), (1, 1, 2))
+        else:
+            Thi_n = Zc.reshape(Bn, k, 2, K * a1, r)
+            if Thi_n.dtype != self.dtype:
+                Thi_n = Thi_n.to(self.dtype)
+        return Tlo_n, Thi_n
+
+    # ------------------------------------------------------------------------------------------
+    # R4: one step of the left-to-right QR sweep        TNNOptimizer.py:87-108
+    # ------------------------------------------------------------------------------------------
+    def qr_step(self, Ti, Tn):
+        """Ti [B,l,2,a,r] -> isometry Q (same shape); Tn [B,r,2,a',r'] <- R . Tn."""
+        p = self.p
+        Bn, l, _, a, r = Ti.shape
+        Alast, Xs, R = self.orth_cols(Ti, (1, 3, 1))
+        Q = self._empty(Ti.shape, Ti)
+        p.contract(Alast, (1, 3, 1), Xs.to(self.dtype).permute(0, 2, 1), (1, 1, 1), Q, (1, 3, 1), conjB=True)
+        Tn_new = self._empty(Tn.shape, Tn)
+        p.contract(R.to(self.dtype), (1, 1, 1), Tn, (1, 1, 3), Tn_new, (1, 1, 3))
+        return Q, Tn_new
+
+    # ------------------------------------------------------------------------------------------
+    # R5: one step of the right-to-left bond (chi) truncation      TNNOptimizer.py:111-134
+    # ------------------------------------------------------------------------------------------
+    def bond_svd_step(self, Tl, Tr, chi, max_err=None):
+        """Tl [B,l',2,a',l] (left-isometric), Tr [B,l,2,a,r]. Theta = Tl.Tr is truncated to chi singular
+        values (and optionally to the relative error max_err); returns (Tl.U sqrt(S), sqrt(S) Vh, s_discarded)."""
+        p = self.p
+        Bn, l, _, a, r = Tr.shape
+        Mlast, F, Lh = self.orth_rows(Tr, (1, 1, 3))
+        Uh_L, s, Wh_L = self._svd_core(Lh)
+        k = self._keep(s, chi, max_err, True)
+        disc = s[:, k:].clone()
+        # Tr' = sqrt(S_k) Wh_L[:k] F Mlast
+        WF = torch.empty((Bn, k, l), dtype=self.dtype, device=Tr.device)
+        p.contract(p.rowscale(Wh_L, s, k, 0.5, 0.0, 0, C128), (1, 1, 1), F, (1, 1, 1), WF, (1, 1, 1))
+        Tr_n = self._empty((Bn, k, 2, a, r), Tr)
+        p.contract(WF, (1, 1, 1), Mlast, (1, 1, 3), Tr_n, (1, 1, 3))
+        # Tl' = Tl . U_L[:, :k] sqrt(S_k):  U_L[r,j] sqrt(s_j) = conj(UL[j,r])
+        UL = p.rowscale(Uh_L, s, k, 0.5, 0.0, 0, self.dtype)
+        Tl_n = self._empty(tuple(Tl.shape[:4]) + (k,), Tl)
+        p.contract(Tl, (1, 3, 1), UL.permute(0, 2, 1), (1, 1, 1), Tl_n, (1, 3, 1), conjB=True)
+        return Tl_n, Tr_n, disc
+
+    # ------------------------------------------------------------------------------------------
+    # R3: inner-index (kappa) truncation                 TNNOptimizer.py:164-197
+    # ------------------------------------------------------------------------------------------
+    def kappa_truncate(self, T, kappa, max_err=None):
+        """T [B,l,2,a,r] -> U.S over the inner index: [B,l,2,k,r], k = min(kappa, a) (and the relative rule)."""
+        p = self.p
+        Bn, l, _, a, r = T.shape
+        Tv = T.permute(0, 1, 2, 4, 3)                           # [b | l,s,r | a]
+        G = self._gram_cols(Tv, (1, 3, 1))                      # G = T^h T over (l,s,r)
+        lam, Vh = p.eigh_psd(G, self.jacobi_tol)
+        k = self._keep(lam, kappa, max_err, True, squared=True)
+        disc = lam[:, k:].clamp_min(0).sqrt()
+        # T'[l,s,j,r] = sum_a conj(Vh[j,a]) T[l,s,a,r]
+        Vk = Vh[:, :k, :].to(self.dtype)
+        T_n = self._empty((Bn, l, 2, k, r), T)
+        p.contract(Vk, (1, 1, 1), T.permute(0, 3, 1, 2, 4), (1, 1, 3), T_n.permute(0, 3, 1, 2, 4), (1, 1, 3), conjA=True)
+        return T_n, disc
+
+    # ------------------------------------------------------------------------------------------
+    # truncate layer = bondTruncate + svdKappa          Circuit.py:476-481
+    # ------------------------------------------------------------------------------------------
+    def qr_left2right(self, Ts):
+        for i in range(len(Ts) - 1):
+            Ts[i], Ts[i + 1] = self.qr_step(Ts[i], Ts[i + 1])
+
+    def svd_right2left(self, Ts, chi, max_err=None):
+        disc = []
+        for i in range(len(Ts) - 1, 0, -1):
+            Ts[i - 1], Ts[i], d = self.bond_svd_step(Ts[i - 1], Ts[i], chi, max_err)
+            disc.append(d)
+        return disc
+
+    def svd_kappa(self, Ts, kappa, max_err=None, has_inner=None):
+        for i, T in enumerate(Ts):
+            if kappa is not None and ((has_inner is not None and not has_inner[i]) or T.shape[3] <= kappa):
+                continue
+            Ts[i], _ = self.kappa_truncate(T, kappa, max_err)
+
+    # ------------------------------------------------------------------------------------------
+    # R7: readout by transfer matrices                   Circuit.py:226-332, dmOperations.py
+    # ------------------------------------------------------------------------------------------
+    def transfer(self, L, T, Tc=None, op=None):
+        """L [B,l,l'] (c128) -> L'[r,r'] = sum L[l,l'] (O.T)[l,s',a,r] conj(Tc[l',s',a,r']),
+        (O.T)[s'] = sum_s O[s',s] T[s]; O = identity if op is None; Tc = T if None."""
+        p = self.p
+        Tc = T if Tc is None else Tc
+        Bn, l, _, a, r = T.shape
+        X = torch.empty((Bn, Tc.shape[1], 2, a, r), dtype=C128, device=T.device)
+        p.contract(L.permute(0, 2, 1), (1, 1, 1), T, (1, 1, 3), X, (1, 1, 3))
+        if op is not None:
+            X = p.absorb_1q(X, op.reshape(-1, 2, 2, 1).to(C128).contiguous())
+        Ln = torch.empty((Bn, r, Tc.shape[4]), dtype=C128, device=T.device)
+        p.contract(X.permute(0, 4, 1, 2, 3), (1, 1, 3), Tc, (1, 3, 1), Ln, (1, 1, 1), conjB=True)
+        return Ln
+
+    def transfer_proj(self, L, T, bit):
+        """Same with both copies projected on |bit><bit| (bit may differ per batch entry: LongTensor [B])."""
+        p = self.p
+        Bn, l, _, a, r = T.shape
+        nL = L.shape[0]
+        Ln = torch.empty((nL, r, r), dtype=C128, device=T.device)
+        bits = torch.as_tensor(bit, device='cpu').reshape(-1).expand(nL) if not isinstance(bit, int) else None
+        groups = [(None, bit)] if bits is None else [((bits == v).nonzero().reshape(-1), v) for v in (0, 1)]
+        for idx, v in groups:
+            if idx is not None and idx.numel() == 0:
+                continue
+            Lg = L if idx is None else L.index_select(0, idx.to(L.device))
+            n = Lg.shape[0]
+            Tb = T[:, :, v]                                      # [B,l,a,r]
+            if Bn == 1:
+                Tb = Tb.expand(n, l, a, r)
+            elif idx is not None:
+                Tb = Tb.index_select(0, idx.to(T.device))
+            X = torch.empty((n, l, a, r), dtype=C128, device=T.device)
+            p.contract(Lg.permute(0, 2, 1), (1, 1, 1), Tb, (1, 1, 2), X, (1, 1, 2))
+            out = torch.empty((n, r, r), dtype=C128, device=T.device)
+            p.contract(X.permute(0, 3, 1, 2), (1, 1, 2), Tb, (1, 2, 1), out, (1, 1, 1), conjB=True)
+            if idx is None:
+                Ln = out
+            else:
+                Ln.index_copy_(0, idx.to(L.device), out)
+        return Ln
+
+    def chain_value(self, Ts, ops=None, Tcs=None):
+        """Tr(prod_k O_k rho) for the un-normalised MPDO (ops: {site: 2x2 tensor}); returns [B] complex128."""
+        ops = ops or {}
+        Bn = Ts[0].shape[0]
+        L = torch.ones((Bn, 1, 1), dtype=C128, device=Ts[0].device)
+        for k, T in enumerate(Ts):
+            L = self.transfer(L, T, None if Tcs is None else Tcs[k], ops.get(k))
+        return L.reshape(Bn)
+
+    def bitstring_probs(self, Ts, bits):
+        """<b|rho|b> for bitstrings bits [NB, n] (0/1 ints) of one circuit (B = 1) -> [NB] float64."""
+        bits = torch.as_tensor(bits).reshape(-1, len(Ts))
+        nb = bits.shape[0]
+        L = torch.ones((nb, 1, 1), dtype=C128, device=Ts[0].device)
+        for k, T in enumerate(Ts):
+            L = self.transfer_proj(L, T, bits[:, k])
+        return L.reshape(nb).real
+
+    def dense_rho(self, Ts):
+        """Dense un-normalised rho [B, 2^n, 2^n] (small n only)."""
+        p = self.p
+        Bn = Ts[0].shape[0]
+        n = len(Ts)
+        Rm = torch.ones((Bn, 1, 1, 1), dtype=C128, device=Ts[0].device)  # [B, P, l, l']
+        for T in Ts:
+            _, l, _, a, r = T.shape
+            P = Rm.shape[1]
+            # Y[b,P,l',s,a,r] = sum_l R[b,P,l,l'] T[b,l,s,a,r]
+            Y = torch.empty((Bn, P, l, 2, a, r), dtype=C128, device=T.device)
+            p.contract(Rm.permute(0, 1, 3, 2), (1, 2, 1), T, (1, 1, 3), Y.reshape(Bn, P, l, 2 * a * r), (1, 2, 1))
+            # R'[b,P,s,s',r,r'] = sum_{l',a} Y[b,P,l',s,a,r] conj(T[b,l',s',a,r'])
+            Rn = torch.empty((Bn, P, 2, 2, r, r), dtype=C128, device=T.device)
+            p.contract(Y.permute(0, 1, 3, 5, 2, 4), (1, 3, 2), T.permute(0, 1, 3, 2, 4), (1, 2, 2),
+                       Rn.permute(0, 1, 2, 4, 3, 5), (1, 3, 2), conjB=True)
+            Rm = Rn.reshape(Bn, P * 4, r, r)
+        rho = Rm.reshape([Bn] + [2, 2] * n)
+        perm = [0] + [1 + 2 * i for i in range(n)] + [2 + 2 * i for i in range(n)]
+        return rho.permute(perm).reshape(Bn, 2 ** n, 2 ** n)
+
+    def dense_vector(self, Ts):
+        """Dense state vector [B, 2^n] of an ideal circuit (inner dims all 1)."""
+        p = self.p
+        Bn = Ts[0].shape[0]
+        V = torch.ones((Bn, 1, 1), dtype=C128, device=Ts[0].device)
+        for T in Ts:
+            _, l, _, a, r = T.shape
+            assert a == 1, 'state vector readout needs an ideal (noise-free) state'
+            Vn = torch.empty((Bn, V.shape[1], 2 * r), dtype=C128, device=T.device)
+            p.contract(V, (1, 1, 1), T.reshape(Bn, l, 2 * r), (1, 1, 1), Vn, (1, 1, 1))
+            V = Vn.reshape(Bn, -1, r)
+        return V.reshape(Bn, -1)

@@ -1,0 +1,72 @@
+// Shared helpers for the mpdo_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/mpdo_b200.h"
+
+namespace mpdo {
+
+extern thread_local char g_err[512];
+extern long long g_launches;
+
+inline int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  ++g_launches;
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+#define MPDO_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      snprintf(mpdo::g_err, sizeof(mpdo::g_err), "%s: %s", #call, cudaGetErrorString(e_)); \
+      return (int)e_;                                                                     \
+    }                                                                                     \
+  } while (0)
+
+// ---- complex helpers (interleaved re/im in float2 / double2) -------------------------------
+template <typename R> struct cplx;
+template <> struct cplx<float> { using type = float2; };
+template <> struct cplx<double> { using type = double2; };
+
+template <typename C> struct real_of;
+template <> struct real_of<float2> { using type = float; };
+template <> struct real_of<double2> { using type = double; };
+
+template <typename CO, typename CI> __device__ __forceinline__ CO cconv(CI v) {
+  CO o;
+  o.x = (typename real_of<CO>::type)v.x;
+  o.y = (typename real_of<CO>::type)v.y;
+  return o;
+}
+
+// acc += a * b
+template <typename C> __device__ __forceinline__ void cfma(C& acc, const C a, const C b) {
+  acc.x = fma(a.x, b.x, acc.x);
+  acc.x = fma(-a.y, b.y, acc.x);
+  acc.y = fma(a.x, b.y, acc.y);
+  acc.y = fma(a.y, b.x, acc.y);
+}
+
+__device__ __forceinline__ long long map_idx(const mpdo_idxmap& m, int i) {
+  if (m.d0 <= 0) return (long long)i * m.s0;
+  int i0 = i % m.d0;
+  int t = i / m.d0;
+  if (m.d1 <= 0) return (long long)i0 * m.s0 + (long long)t * m.s1;
+  int i1 = t % m.d1;
+  int i2 = t / m.d1;
+  return (long long)i0 * m.s0 + (long long)i1 * m.s1 + (long long)i2 * m.s2;
+}
+
+}  // namespace mpdo

@@ -1,0 +1,230 @@
+// Batched complex tensor contraction for MPDO site tensors (sm_100a).
+//
+//   C[b,i,j] = alpha * sum_k opA(A[b,i,k]) * opB(B[b,k,j]) + beta * C[b,i,j]
+//
+// Every logical axis is a composite index (mpdo_idxmap) over up to three axes of the operand, so the
+// same kernel performs the two-site bond merge, the R-absorb of the QR sweep, Gram matrices over any
+// grouping of T[l,s,a,r], the projected updates U^h*Theta of the bond/kappa truncation and the
+// transfer-matrix steps of the readout without a transpose pass through HBM.
+//
+// Tiling: 64x64 output tile per CTA, K staged through shared memory in slabs of 16, 256 threads each
+// owning a 4x4 interleaved micro-tile of complex accumulators (rows ty+16u, columns tx+16v, so both the
+// shared-memory reads and the global stores of a warp are stride-1). Global loads are issued one tile
+// ahead into registers; the loader picks the thread->element mapping that makes the contiguous axis of
+// each operand the fastest-varying one. complex64 operands may be accumulated in fp32 (FFMA) or fp64
+// (DFMA; B200 runs fp64 at half the fp32 rate, which is what makes fp64 Gram matrices affordable).
+#include "common.cuh"
+
+namespace mpdo {
+
+constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+constexpr int TM = BM / 16, TN = BN / 16;
+
+template <typename TA, typename TB, typename TC, typename R>
+__global__ void __launch_bounds__(NT) contract_kernel(const mpdo_contract_desc d, const TA* __restrict__ A,
+                                                      const TB* __restrict__ B, TC* __restrict__ C, int tilesM,
+                                                      int tilesN, int kChunk) {
+  using CR = typename cplx<R>::type;
+  __shared__ CR As[BK][BM + 1];
+  __shared__ CR Bs[BK][BN + 1];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+
+  long long t = blockIdx.x;
+  const int tn = (int)(t % tilesN);
+  t /= tilesN;
+  const int tm = (int)(t % tilesM);
+  t /= tilesM;
+  const int ksplit = d.ksplit > 1 ? d.ksplit : 1;
+  const int ks = (int)(t % ksplit);
+  const int b = (int)(t / ksplit);
+
+  const int i0 = tm * BM, j0 = tn * BN;
+  const int kBeg = ks * kChunk;
+  const int kEnd = min(d.K, kBeg + kChunk);
+
+  const TA* Ab = A + map_idx(d.Ab, b);
+  const TB* Bb = B + map_idx(d.Bb, b);
+
+  // ---- loader geometry -----------------------------------------------------------------------
+  constexpr int LA = BM * BK / NT;  // elements of the A tile per thread
+  constexpr int LB = BN * BK / NT;
+  const bool akf = d.a_kfast != 0;
+  const bool bjf = d.b_jfast != 0;
+  // A, k fastest: kk fixed per thread, rows ii0 + r*(NT/BK).  A, i fastest: ii fixed, k = kk0 + r*(NT/BM).
+  const int a_kk = akf ? tid % BK : tid / BM;
+  const int a_ii = akf ? tid / BK : tid % BM;
+  const int b_kk = bjf ? tid / BN : tid % BK;
+  const int b_jj = bjf ? tid % BN : tid / BK;
+
+  long long offAi[LA];
+  long long offBj[LB];
+#pragma unroll
+  for (int r = 0; r < LA; ++r) {
+    int i = i0 + (akf ? a_ii + r * (NT / BK) : a_ii);
+    offAi[r] = (i < d.M) ? map_idx(d.Ai, i) : -1;
+  }
+#pragma unroll
+  for (int r = 0; r < LB; ++r) {
+    int j = j0 + (bjf ? b_jj : b_jj + r * (NT / BK));
+    offBj[r] = (j < d.N) ? map_idx(d.Bj, j) : -1;
+  }
+
+  CR ra[LA], rb[LB];
+  auto load_tile = [&](int k0) {
+#pragma unroll
+    for (int r = 0; r < LA; ++r) {
+      int k = k0 + (akf ? a_kk : a_kk + r * (NT / BM));
+      CR v;
+      v.x = 0;
+      v.y = 0;
+      if (k < kEnd && offAi[r] >= 0) {
+        v = cconv<CR>(Ab[offAi[r] + map_idx(d.Ak, k)]);
+        if (d.conjA) v.y = -v.y;
+      }
+      ra[r] = v;
+    }
+#pragma unroll
+    for (int r = 0; r < LB; ++r) {
+      int k = k0 + (bjf ? b_kk + r * (NT / BN) : b_kk);
+      CR v;
+      v.x = 0;
+      v.y = 0;
+      if (k < kEnd && offBj[r] >= 0) {
+        v = cconv<CR>(Bb[offBj[r] + map_idx(d.Bk, k)]);
+        if (d.conjB) v.y = -v.y;
+      }
+      rb[r] = v;
+    }
+  };
+  auto store_tile = [&]() {
+#pragma unroll
+    for (int r = 0; r < LA; ++r) {
+      if (akf)
+        As[a_kk][a_ii + r * (NT / BK)] = ra[r];
+      else
+        As[a_kk + r * (NT / BM)][a_ii] = ra[r];
+    }
+#pragma unroll
+    for (int r = 0; r < LB; ++r) {
+      if (bjf)
+        Bs[b_kk + r * (NT / BN)][b_jj] = rb[r];
+      else
+        Bs[b_kk][b_jj + r * (NT / BK)] = rb[r];
+    }
+  };
+
+  CR acc[TM][TN];
+#pragma unroll
+  for (int u = 0; u < TM; ++u)
+#pragma unroll
+    for (int v = 0; v < TN; ++v) {
+      acc[u][v].x = 0;
+      acc[u][v].y = 0;
+    }
+
+  if (kBeg < kEnd) {
+    load_tile(kBeg);
+    store_tile();
+    __syncthreads();
+    for (int k0 = kBeg; k0 < kEnd; k0 += BK) {
+      const bool more = (k0 + BK) < kEnd;
+      if (more) load_tile(k0 + BK);
+#pragma unroll
+      for (int kk = 0; kk < BK; ++kk) {
+        CR a[TM], bb[TN];
+#pragma unroll
+        for (int u = 0; u < TM; ++u) a[u] = As[kk][ty + 16 * u];
+#pragma unroll
+        for (int v = 0; v < TN; ++v) bb[v] = Bs[kk][tx + 16 * v];
+#pragma unroll
+        for (int u = 0; u < TM; ++u)
+#pragma unroll
+          for (int v = 0; v < TN; ++v) cfma(acc[u][v], a[u], bb[v]);
+      }
+      __syncthreads();
+      if (more) {
+        store_tile();
+        __syncthreads();
+      }
+    }
+  }
+
+  // ---- epilogue --------------------------------------------------------------------------------
+  using RC = typename real_of<TC>::type;
+  TC* Cb = C + map_idx(d.Cb, b);
+  long long offCj[TN];
+#pragma unroll
+  for (int v = 0; v < TN; ++v) {
+    int j = j0 + tx + 16 * v;
+    offCj[v] = (j < d.N) ? map_idx(d.Cj, j) : -1;
+  }
+  const R alpha = (R)d.alpha;
+  const R beta = (R)d.beta;
+#pragma unroll
+  for (int u = 0; u < TM; ++u) {
+    int i = i0 + ty + 16 * u;
+    if (i >= d.M) continue;
+    long long oi = map_idx(d.Ci, i);
+#pragma unroll
+    for (int v = 0; v < TN; ++v) {
+      if (offCj[v] < 0) continue;
+      TC* p = Cb + oi + offCj[v];
+      R re = alpha * acc[u][v].x, im = alpha * acc[u][v].y;
+      if (ksplit > 1) {
+        atomicAdd(&p->x, (RC)re);
+        atomicAdd(&p->y, (RC)im);
+      } else {
+        if (beta != (R)0) {
+          TC old = *p;
+          re += beta * (R)old.x;
+          im += beta * (R)old.y;
+        }
+        TC o;
+        o.x = (RC)re;
+        o.y = (RC)im;
+        *p = o;
+      }
+    }
+  }
+}
+
+template <typename TA, typename TB, typename TC, typename R>
+static int launch_contract(const mpdo_contract_desc& d, const void* A, const void* B, void* C, cudaStream_t st) {
+  const int tilesM = (d.M + BM - 1) / BM, tilesN = (d.N + BN - 1) / BN;
+  const int ksplit = d.ksplit > 1 ? d.ksplit : 1;
+  int kChunk = (d.K + ksplit - 1) / ksplit;
+  kChunk = ((kChunk + BK - 1) / BK) * BK;
+  long long grid = (long long)tilesM * tilesN * ksplit * d.batch;
+  if (grid <= 0) return 0;
+  if (grid > 2147483647LL) return fail(MPDO_EINVAL, "mpdo_contract: grid too large");
+  contract_kernel<TA, TB, TC, R><<<(unsigned)grid, NT, 0, st>>>(d, (const TA*)A, (const TB*)B, (TC*)C, tilesM,
+                                                                  tilesN, kChunk);
+  return check_launch("contract_kernel");
+}
+
+}  // namespace mpdo
+
+extern "C" int mpdo_contract(const mpdo_contract_desc* dp, const void* A, const void* B, void* C, void* stream) {
+  using namespace mpdo;
+  if (!dp || !A || !B || !C) return fail(MPDO_EINVAL, "mpdo_contract: null argument");
+  const mpdo_contract_desc& d = *dp;
+  if (d.M < 0 || d.N < 0 || d.K < 0 || d.batch < 0) return fail(MPDO_EINVAL, "mpdo_contract: negative extent");
+  if (d.M == 0 || d.N == 0 || d.batch == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int key = (d.dtypeA << 2) | (d.dtypeB << 1) | d.dtypeC;
+  const bool f64 = d.acc64 || key != 0;
+  if (!f64) return launch_contract<float2, float2, float2, float>(d, A, B, C, st);
+  switch (key) {
+    case 0: return launch_contract<float2, float2, float2, double>(d, A, B, C, st);
+    case 1: return launch_contract<float2, float2, double2, double>(d, A, B, C, st);
+    case 2: return launch_contract<float2, double2, float2, double>(d, A, B, C, st);
+    case 3: return launch_contract<float2, double2, double2, double>(d, A, B, C, st);
+    case 4: return launch_contract<double2, float2, float2, double>(d, A, B, C, st);
+    case 5: return launch_contract<double2, float2, double2, double>(d, A, B, C, st);
+    case 6: return launch_contract<double2, double2, float2, double>(d, A, B, C, st);
+    case 7: return launch_contract<double2, double2, double2, double>(d, A, B, C, st);
+  }
+  return fail(MPDO_EINVAL, "mpdo_contract: bad dtype");
+}

@@ -1,0 +1,337 @@
+// Batched one-sided (Hestenes) Jacobi orthogonalisation of the rows of small complex matrices, the
+// core of every SVD / Hermitian eigen-decomposition on the MPDO truncation path (sm_100a).
+//
+// A matrix Y (n rows) is partitioned into blocks of b rows. One CTA owns one pair of blocks: it
+// stages the 2b rows in shared memory, one warp per row pair rotates them (dot products with
+// warp-shuffle reductions, then the 2x2 unitary applied in place), and writes the rows back. Block
+// pairs of one round are disjoint (round-robin tournament), so a round is one launch over
+// (pairs, batch); a sweep is nbp-1 rounds. When the whole matrix fits one block pair the sweeps are
+// looped inside the kernel and a decomposition is a single launch.
+//
+// Everything is fp64: B200 issues DFMA at half the FFMA rate, and fp64 cores make the complex64
+// path insensitive to the conditioning of the Gram matrices it feeds in here.
+#include "common.cuh"
+
+namespace mpdo {
+
+struct JacobiArgs {
+  int n, m, mt, ld;
+  long long batchStride;
+  int b;       // rows per block (= warps per CTA)
+  int nbp;     // number of blocks rounded up to even
+  int round;   // tournament round (multi-launch mode)
+  int sweep;   // sweep index (multi-launch mode)
+  int maxSweeps;
+  int loop;    // 1: whole matrix in this CTA, loop sweeps in-kernel
+  double tol;
+  int* cnt;    // [batch][WORK_INTS]: 32 per-sweep rotation counters, then one double = max row norm^2
+};
+
+constexpr int WORK_INTS = 48;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Rotate rows x, y (shared memory) so that their first m entries become orthogonal. Returns 1 if a
+// rotation was applied.
+__device__ __forceinline__ int rotate_pair(double2* x, double2* y, int m, int mt, double tol, double floor2,
+                                           int lane) {
+  double a = 0, bq = 0, gr = 0, gi = 0;
+  for (int k = lane; k < m; k += 32) {
+    double2 u = x[k], v = y[k];
+    a = fma(u.x, u.x, fma(u.y, u.y, a));
+    bq = fma(v.x, v.x, fma(v.y, v.y, bq));
+    // g = sum x * conj(y)
+    gr = fma(u.x, v.x, fma(u.y, v.y, gr));
+    gi = fma(u.y, v.x, fma(-u.x, v.y, gi));
+  }
+  a = warp_sum(a);
+  bq = warp_sum(bq);
+  gr = warp_sum(gr);
+  gi = warp_sum(gi);
+  const double g2 = gr * gr + gi * gi;
+  const double ab = a * bq;
+  // rows that are both at rounding level of the matrix scale carry no information: leave them alone
+  if (!(ab > floor2) || !(g2 > tol * tol * ab)) return 0;
+  const double g = sqrt(g2);
+  const double zeta = (bq - a) / (2.0 * g);
+  const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+  const double c = rsqrt(1.0 + tt * tt);
+  const double s = c * tt;
+  // phase e^{i phi} = g / |g|
+  const double pr = gr / g, pi = gi / g;
+  // x' = c x - s e^{i phi} y ; y' = s e^{-i phi} x + c y
+  const double sr = s * pr, si = s * pi;
+  for (int k = lane; k < mt; k += 32) {
+    double2 u = x[k], v = y[k];
+    double2 xn, yn;
+    xn.x = c * u.x - (sr * v.x - si * v.y);
+    xn.y = c * u.y - (sr * v.y + si * v.x);
+    yn.x = (sr * u.x + si * u.y) + c * v.x;
+    yn.y = (sr * u.y - si * u.x) + c * v.y;
+    x[k] = xn;
+    y[k] = yn;
+  }
+  return 1;
+}
+
+// Round-robin partner tables: `np` players (even), round r in [0, np-1), pair q in [0, np/2).
+__device__ __forceinline__ void rr_pair(int np, int r, int q, int& p0, int& p1) {
+  if (q == 0) {
+    p0 = np - 1;
+    p1 = r % (np - 1);
+  } else {
+    p0 = (r + q) % (np - 1);
+    p1 = (r - q + 2 * (np - 1)) % (np - 1);
+  }
+}
+
+__global__ void __launch_bounds__(1024) jacobi_kernel(JacobiArgs p, double2* __restrict__ Yall) {
+  extern __shared__ double2 smem[];  // 2b rows of mt entries
+  __shared__ int s_any;
+  const int bidx = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = p.b;
+  int* cnt = p.cnt + (long long)bidx * WORK_INTS;
+  const double amax = *reinterpret_cast<const double*>(cnt + 32);
+  const double floor2 = fmax(1e-290, 1e-48 * amax * amax);
+
+  if (!p.loop && p.sweep > 0 && cnt[p.sweep - 1] == 0) return;  // converged in the previous sweep
+
+  int I, J;
+  if (p.loop) {
+    I = 0;
+    J = 1;
+  } else {
+    rr_pair(p.nbp, p.round, blockIdx.x, I, J);
+  }
+  double2* Y = Yall + (long long)bidx * p.batchStride;
+
+  // stage the 2b rows
+  for (int v = warp; v < 2 * b; v += b) {
+    int row = (v < b) ? I * b + v : J * b + (v - b);
+    double2* dst = smem + (long long)v * p.mt;
+    if (row < p.n) {
+      const double2* src = Y + (long long)row * p.ld;
+      for (int k = lane; k < p.mt; k += 32) dst[k] = src[k];
+    }
+  }
+  __syncthreads();
+
+  const int be = (b + 1) & ~1;  // b rounded up to even for the intra-block tournament
+  const int nsweeps = p.loop ? p.maxSweeps : 1;
+  for (int sw = 0; sw < nsweeps; ++sw) {
+    int rot = 0;
+    if (p.loop || p.round == 0) {
+      // intra-block pairs of both blocks: be/2 pairs per block per step, be-1 steps
+      for (int step = 0; step < be - 1; ++step) {
+        for (int w = warp; w < be; w += b) {
+          int blk = w / (be / 2), q = w % (be / 2);
+          int a0, a1;
+          rr_pair(be, step, q, a0, a1);
+          int r0 = (blk ? J : I) * b + a0, r1 = (blk ? J : I) * b + a1;
+          if (a0 < b && a1 < b && r0 < p.n && r1 < p.n)
+            rot |= rotate_pair(smem + (long long)(blk * b + a0) * p.mt, smem + (long long)(blk * b + a1) * p.mt, p.m,
+                               p.mt, p.tol, floor2, lane);
+        }
+        __syncthreads();
+      }
+    }
+    // cross pairs: warp w pairs row w of block I with row (w+step)%b of block J
+    for (int step = 0; step < b; ++step) {
+      int a0 = warp, a1 = (warp + step) % b;
+      int r0 = I * b + a0, r1 = J * b + a1;
+      if (r0 < p.n && r1 < p.n)
+        rot |= rotate_pair(smem + (long long)a0 * p.mt, smem + (long long)(b + a1) * p.mt, p.m, p.mt, p.tol, floor2, lane);
+      __syncthreads();
+    }
+    if (p.loop) {
+      if (threadIdx.x == 0) s_any = 0;
+      __syncthreads();
+      if (rot && lane == 0) atomicOr(&s_any, 1);
+      __syncthreads();
+      int any = s_any;
+      __syncthreads();
+      if (threadIdx.x == 0) cnt[sw] = any;
+      if (!any) break;
+    } else {
+      if (rot && lane == 0) atomicAdd(&cnt[p.sweep], 1);
+    }
+  }
+
+  // write back
+  for (int v = warp; v < 2 * b; v += b) {
+    int row = (v < b) ? I * b + v : J * b + (v - b);
+    if (row < p.n) {
+      double2* dst = Y + (long long)row * p.ld;
+      const double2* src = smem + (long long)v * p.mt;
+      for (int k = lane; k < p.mt; k += 32) dst[k] = src[k];
+    }
+  }
+}
+
+// max over rows of |row[0..m)|^2, stored as a double after the 32 sweep counters of each batch entry
+__global__ void __launch_bounds__(256) row_norm_max_kernel(int n, int m, int ld, long long batchStride,
+                                                           const double2* __restrict__ Yall, int* __restrict__ work) {
+  __shared__ double wmax[8];
+  const int bidx = blockIdx.x;
+  const double2* Y = Yall + (long long)bidx * batchStride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  double best = 0;
+  for (int r = warp; r < n; r += nw) {
+    const double2* row = Y + (long long)r * ld;
+    double a = 0;
+    for (int k = lane; k < m; k += 32) {
+      double2 u = row[k];
+      a = fma(u.x, u.x, fma(u.y, u.y, a));
+    }
+    a = warp_sum(a);
+    best = fmax(best, a);
+  }
+  if (lane == 0) wmax[warp] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < nw; ++w) best = fmax(best, wmax[w]);
+    *reinterpret_cast<double*>(work + (long long)bidx * WORK_INTS + 32) = best;
+  }
+}
+
+// ---- finalize: norms, descending sort, optional normalised rows / accumulator ------------------
+__global__ void __launch_bounds__(256) rows_finalize_kernel(int n, int m, int mz, int ld, long long batchStride,
+                                                            const double2* __restrict__ Yall, double* __restrict__ sOut,
+                                                            double2* __restrict__ Yn, double2* __restrict__ Z,
+                                                            int normalize, double zeroTol) {
+  extern __shared__ double fsm[];  // norms[n], then int rank[n]
+  double* norms = fsm;
+  int* rank = (int*)(fsm + n);
+  const int bidx = blockIdx.x;
+  const double2* Y = Yall + (long long)bidx * batchStride;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int r = warp; r < n; r += nw) {
+    const double2* row = Y + (long long)r * ld;
+    double a = 0;
+    for (int k = lane; k < m; k += 32) {
+      double2 u = row[k];
+      a = fma(u.x, u.x, fma(u.y, u.y, a));
+    }
+    a = warp_sum(a);
+    if (lane == 0) norms[r] = sqrt(a);
+  }
+  __syncthreads();
+  for (int r = threadIdx.x; r < n; r += blockDim.x) {
+    double v = norms[r];
+    int rk = 0;
+    for (int q = 0; q < n; ++q) {
+      double w = norms[q];
+      rk += (w > v) || (w == v && q < r);
+    }
+    rank[r] = rk;
+    sOut[(long long)bidx * n + rk] = v;
+  }
+  __syncthreads();
+  double vmax = 0;
+  for (int q = 0; q < n; ++q) vmax = fmax(vmax, norms[q]);
+  for (int r = warp; r < n; r += nw) {
+    const double2* row = Y + (long long)r * ld;
+    const int rk = rank[r];
+    const double nv = norms[r];
+    if (Yn) {
+      double sc = 1.0;
+      if (normalize) sc = (nv > zeroTol * vmax && nv > 0) ? 1.0 / nv : 0.0;
+      double2* dst = Yn + ((long long)bidx * n + rk) * m;
+      for (int k = lane; k < m; k += 32) {
+        double2 u = row[k];
+        u.x *= sc;
+        u.y *= sc;
+        dst[k] = u;
+      }
+    }
+    if (Z) {
+      double2* dst = Z + ((long long)bidx * n + rk) * mz;
+      for (int k = lane; k < mz; k += 32) dst[k] = row[m + k];
+    }
+  }
+}
+
+}  // namespace mpdo
+
+extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t batchStride, void* Y, double tol,
+                                int maxSweeps, int32_t* work, void* stream) {
+  using namespace mpdo;
+  if (batch <= 0 || n <= 0) return 0;
+  if (!Y || !work || m <= 0 || mt < m || ld < mt) return fail(MPDO_EINVAL, "mpdo_jacobi_rows: bad argument");
+  if (maxSweeps < 1) maxSweeps = 1;
+  if (maxSweeps > 32) maxSweeps = 32;
+  cudaStream_t st = (cudaStream_t)stream;
+  MPDO_CUDA(cudaMemsetAsync(work, 0, sizeof(int32_t) * WORK_INTS * (size_t)batch, st));
+  if (n == 1) return 0;
+  if (batch > 65535) return fail(MPDO_EINVAL, "mpdo_jacobi_rows: batch > 65535");
+  row_norm_max_kernel<<<batch, 256, 0, st>>>(n, m, ld, batchStride, (const double2*)Y, work);
+  {
+    int rc = check_launch("row_norm_max_kernel");
+    if (rc) return rc;
+  }
+
+  static int smemMax = 0;
+  if (!smemMax) {
+    int dev = 0;
+    MPDO_CUDA(cudaGetDevice(&dev));
+    MPDO_CUDA(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
+  }
+  const long long rowBytes = (long long)mt * sizeof(double2);
+  int bmax = (int)((smemMax - 1024) / (2 * rowBytes));
+  if (bmax < 1) return fail(MPDO_ENOSMEM, "mpdo_jacobi_rows: a row pair does not fit shared memory");
+  int b = bmax < 32 ? bmax : 32;
+  const int half = (n + 1) / 2;
+  if (b > half) b = half;
+  const int nb = (n + b - 1) / b;
+  const int nbp = (nb + 1) & ~1;
+
+  JacobiArgs a;
+  a.n = n;
+  a.m = m;
+  a.mt = mt;
+  a.ld = ld;
+  a.batchStride = batchStride;
+  a.b = b;
+  a.nbp = nbp;
+  a.round = 0;
+  a.sweep = 0;
+  a.maxSweeps = maxSweeps;
+  a.tol = tol;
+  a.cnt = work;
+  const size_t smem = (size_t)(2 * b) * rowBytes;
+  const unsigned threads = 32u * b;
+  if (nbp == 2) {
+    a.loop = 1;
+    jacobi_kernel<<<dim3(1, batch), threads, smem, st>>>(a, (double2*)Y);
+    return check_launch("jacobi_kernel(loop)");
+  }
+  a.loop = 0;
+  for (int sw = 0; sw < maxSweeps; ++sw) {
+    a.sweep = sw;
+    for (int r = 0; r < nbp - 1; ++r) {
+      a.round = r;
+      jacobi_kernel<<<dim3(nbp / 2, batch), threads, smem, st>>>(a, (double2*)Y);
+      int rc = check_launch("jacobi_kernel");
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+extern "C" int mpdo_rows_finalize(int batch, int n, int m, int mz, int ld, int64_t batchStride, const void* Y,
+                                  double* s, void* Yn, void* Z, int normalize, double zeroTol, void* stream) {
+  using namespace mpdo;
+  if (batch <= 0 || n <= 0) return 0;
+  if (!Y || !s || m <= 0) return fail(MPDO_EINVAL, "mpdo_rows_finalize: bad argument");
+  const size_t smem = (size_t)n * (sizeof(double) + sizeof(int));
+  if (smem > 48 * 1024) return fail(MPDO_ENOSMEM, "mpdo_rows_finalize: n too large");
+  rows_finalize_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(n, m, mz, ld, batchStride, (const double2*)Y, s,
+                                                                  (double2*)Yn, (double2*)Z, normalize, zeroTol);
+  return check_launch("rows_finalize_kernel");
+}
