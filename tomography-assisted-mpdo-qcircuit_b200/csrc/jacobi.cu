@@ -280,7 +280,7 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
     int dev = 0;
     MPDO_CUDA(cudaGetDevice(&dev));
     MPDO_CUDA(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax));
+    MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024));
   }
   const long long rowBytes = (long long)mt * sizeof(double2);
   int bmax = (int)((smemMax - 1024) / (2 * rowBytes));
