@@ -1,0 +1,378 @@
+"""TensorCircuit of the B200 build: the reference's evolve / gate absorption / readout / sampling surface
+(MPDOSimulator/Circuit.py) over dense site tensors T_k[B, l, s, a, r] and the CUDA kernels in
+libmpdo_b200.so. The host side stays Python; nothing here computes on the CPU except tiny gate operands.
+
+Behaviour kept from the reference on purpose: `truncate()` is a no-op until every
+neighbouring pair shares a bond; the noise-tensor cache is keyed by gate name; in idealNoise mode a
+variational two-qubit gate raises; in unified mode two-qubit gates carry no noise and in realNoise mode
+single-qubit gates carry none; the rank of a gate split follows ||s|| - ||s[:k]|| <= e * 1e-8.
+Extensions: gate angles may be 1-D tensors (B circuits evolved as one batch), non-neighbouring two-qubit
+gates are rejected up front (the reference accepts them and then breaks in truncate), and
+cal_dm(reduced_index=[...]) really traces those qubits (the reference call raises)."""
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import torch as tc
+from torch.linalg import LinAlgError  # noqa: F401  (part of the reference's error surface)
+
+from . import _engine
+from ._node import DenseNode, replicate_nodes
+from .AbstractCircuit import QuantumCircuit
+from .NoiseChannel import NoiseChannel
+from .QuantumGates.AbstractGate import QuantumGate
+from .QuantumGates.SingleGates import MeasureX, MeasureY
+from .TNNOptimizer import bondTruncate, svdKappa_left2right, checkConnectivity
+from .Tools import count_item
+from .dmOperations import DmNodes
+
+GLOBAL_MINIMUM = 2.718281828459045 * 1e-8
+MAX_ATTEMPTS = 4
+
+
+class TensorCircuit(QuantumCircuit):
+    def __init__(self, qn: int, ideal: bool = True, noiseType: str = 'no',
+                 chiFileDict: Optional[Dict[str, Dict[str, Any]]] = None,
+                 chi: Optional[int] = None, kappa: Optional[int] = None,
+                 max_truncation_err: Optional[float] = None, chip: Optional[str] = None,
+                 dtype: Optional = tc.complex64, device: Optional[Union[str, int]] = None):
+        super(TensorCircuit, self).__init__(
+            noiseFiles=chiFileDict, chi=chi, kappa=kappa, max_truncation_err=max_truncation_err,
+            dtype=dtype, device=device
+        )
+        self.qnumber = qn
+        self.ideal = ideal
+        self.noiseType = noiseType.lower()
+        self.Noise = None
+        if not ideal:
+            if self.noiseType not in ['unified', 'realnoise', 'idealnoise']:
+                raise ValueError(f'Unsupported noise type: {self.noiseType}')
+            self.Noise = NoiseChannel(chip=chip, dtype=dtype, device='cpu')
+            self.unified = self.noiseType == 'unified'
+            self.realNoise = self.noiseType == 'realnoise'
+            self.idealNoise = self.noiseType == 'idealnoise'
+            if self.realNoise:
+                self._load_exp_tensors()
+        self.last_stats = {}
+
+    # ------------------------------------------------------------------------------------------------
+    # gate operands (host) -> device
+    # ------------------------------------------------------------------------------------------------
+    def _engine(self):
+        return _engine.engine_for(self.dtype)
+
+    def _dev(self, t: tc.Tensor) -> tc.Tensor:
+        return t.to(device=self.device, dtype=self.dtype).contiguous()
+
+    @staticmethod
+    def _match_batch(node: DenseNode, Bg: int):
+        if Bg > 1 and node.data.shape[0] == 1:
+            node.data = node.data.expand(Bg, *node.data.shape[1:]).contiguous()
+        elif Bg > 1 and node.data.shape[0] != Bg:
+            raise ValueError(f'batch mismatch: state has {node.data.shape[0]} circuits, gate has {Bg}')
+
+    def _single_operand(self, gate: QuantumGate) -> Tuple[tc.Tensor, bool]:
+        """[Bg, 2, 2, K] operand of a single-qubit gate and whether it carries noise (reference :141-155)."""
+        noisy = (self.idealNoise or self.unified) and not gate.ideal
+        U = gate.tensor
+        if not noisy:
+            G = U.reshape(-1, 2, 2, 1) if U.dim() in (2, 3) and U.shape[-2:] == (2, 2) else None
+            if G is None:
+                raise ValueError(f'single-qubit gate tensor of shape {tuple(U.shape)} cannot be applied without noise axes')
+            return G, False
+
+        def build():
+            Ub = U.reshape(-1, 2, 2)
+            return tc.einsum('nlm, ljk, bji -> bnimk', self.Noise.decayTensor, self.Noise.dephasingTensor,
+                             Ub).reshape(Ub.shape[0], 2, 2, -1)
+
+        if gate.variational:
+            return build(), True
+        return self.noiseTensorDict.setdefault(gate.name, build()), True
+
+    def _double_operand(self, gate: QuantumGate, _oqs: List[int]) -> Tuple[tc.Tensor, bool]:
+        """[Bg, 2, 2, 2, 2, K] operand in (lo, hi) qubit order and whether it adds an inner index (:84-99)."""
+        noisy = (self.idealNoise and not gate.ideal) or self.realNoise
+        G = gate.tensor
+        if noisy and not self.realNoise:
+            if gate.variational:
+                raise ValueError('A variational two-qubit gate cannot carry idealNoise (the reference builds a '
+                                 '5-index tensor with 4 axis names here); use cz/cx/cnot/swap/iswap.')
+            base = G.reshape(-1, 2, 2, 2, 2)
+            G = self.noiseTensorDict.setdefault(
+                gate.name, tc.einsum('ijklp, bklmn -> bijmnp', self.Noise.dpCTensor2, base))
+        elif self.realNoise:
+            if G.dim() != 5:
+                raise ValueError('realNoise mode needs a (2,2,2,2,K) two-qubit gate tensor (CZEXP / CPEXP).')
+            G = G.unsqueeze(0)
+        else:
+            if G.shape[-4:] != (2, 2, 2, 2):
+                raise ValueError(f'two-qubit gate tensor of shape {tuple(G.shape)} cannot be applied without a noise axis')
+            G = G.reshape(-1, 2, 2, 2, 2, 1)
+        if _oqs[0] > _oqs[1]:   # gate axes are ordered by _oqs (control first): bring to (lo, hi)
+            G = G.permute(0, 2, 1, 4, 3, 5)
+        return G, noisy
+
+    # ------------------------------------------------------------------------------------------------
+    # gate absorption
+    # ------------------------------------------------------------------------------------------------
+    def _apply_two_qubits_gate(self, _qNodes: List[DenseNode], _qubits, gate: QuantumGate, _oqs: List[int]):
+        """Merge both sites with the (noisy) gate and split back by SVD (reference :74-136)."""
+        if len(_oqs) != 2 or _oqs[0] == _oqs[1]:
+            raise ValueError('Invalid operating qubits for a two-qubit gate.')
+        lo, hi = min(_oqs), max(_oqs)
+        if hi != lo + 1:
+            raise NotImplementedError('two-qubit gates must act on neighbouring qubits (the reference truncation '
+                                      'breaks on long bonds: TNNOptimizer.py:94-95)')
+        G, noisy = self._double_operand(gate, _oqs)
+        G = self._dev(G)
+        for q in (lo, hi):
+            self._match_batch(_qNodes[q], G.shape[0])
+        if _qNodes[lo].data.shape[0] != _qNodes[hi].data.shape[0]:
+            B = max(_qNodes[lo].data.shape[0], _qNodes[hi].data.shape[0])
+            self._match_batch(_qNodes[lo], B)
+            self._match_batch(_qNodes[hi], B)
+        eng = self._engine()
+        _qNodes[lo].data, _qNodes[hi].data = eng.split_2q(_qNodes[lo].data, _qNodes[hi].data, G, GLOBAL_MINIMUM)
+        _qNodes[lo].has_right = True
+        _qNodes[hi].has_left = True
+        if noisy:
+            _qNodes[hi].has_inner = True
+            self.last_stats['noisy_2q_updates'] = self.last_stats.get('noisy_2q_updates', 0) + 1
+
+    def _apply_single_qubit_gate(self, _qNodes: List[DenseNode], _qubits, gate: QuantumGate,
+                                 _oqs: Union[int, List[int]]):
+        """Contract the (noisy) gate into each operating site; the Kraus index joins the inner index (:138-178)."""
+        G, noisy = self._single_operand(gate)
+        G = self._dev(G)
+        eng = self._engine()
+        for q in _oqs:
+            self._match_batch(_qNodes[q], G.shape[0])
+            _qNodes[q].data = eng.absorb_1q(_qNodes[q].data, G)
+            if noisy:
+                _qNodes[q].has_inner = True
+
+    def _add_gate(self, _qubits: List[DenseNode], _layer_num: int, _oqs: List[int], _gate: Optional = None):
+        if not isinstance(_qubits, List):
+            raise TypeError('Qubit must be a list of nodes.')
+        if not isinstance(_oqs, List):
+            raise TypeError('Operating qubits must be a list.')
+        if _oqs[0] is None:
+            return None
+        if max(_oqs) >= self.qnumber:
+            raise ValueError(f'Qubit index out of range, max index is Q{max(_oqs)}.')
+        gate = _gate or self.layers[_layer_num]
+        if not gate or gate.name == 'MeasureZ':
+            return None
+        if not isinstance(gate, QuantumGate):
+            raise TypeError(f'Gate must be a QuantumGate, current type is {type(gate)}.')
+        if not gate.single:
+            self._apply_two_qubits_gate(_qubits, None, gate, _oqs)
+        else:
+            self._apply_single_qubit_gate(_qubits, None, gate, _oqs)
+
+    # ------------------------------------------------------------------------------------------------
+    # evolution
+    # ------------------------------------------------------------------------------------------------
+    def evolve(self, state: List[DenseNode]):
+        """Run every layer on `state` in place (reference :469-491). Host-resident state tensors are uploaded to
+        the circuit's device first; afterwards `state` (aliased as self.stateNodes) lives on the device."""
+        if not isinstance(state, list):
+            raise TypeError('state must be a list of nodes')
+        self._initState = replicate_nodes(state)
+        for node in state:
+            node.data = node.data.to(device=self.device, dtype=self.dtype)
+        self._dm, self._dmNodes, self._vector = None, None, None
+        self.last_stats = {'noisy_2q_updates': 0}
+
+        layers = list(self.layers)   # nn.Sequential indexing is O(n) per access
+        for _i, layer in enumerate(layers):
+            name = layer.name.lower()
+            if 'truncate' in name:
+                if checkConnectivity(state):
+                    bondTruncate(state, max_singular_values=self.chi, max_truncation_err=self.max_truncation_err)
+                    if not self.ideal:
+                        svdKappa_left2right(state, max_singular_values=self.kappa,
+                                            max_truncation_err=self.max_truncation_err)
+            elif 'barrier' in name:
+                pass
+            else:
+                self._add_gate(state, _i, _oqs=self._oqs_list[_i], _gate=layer)
+
+        if not self.ideal and layers and 'truncate' not in layers[-1].name:
+            svdKappa_left2right(state, max_singular_values=self.kappa, max_truncation_err=self.max_truncation_err)
+        self._stateNodes = state
+
+    def forward(self, state: List[DenseNode]):
+        self.evolve(state)
+
+    # ------------------------------------------------------------------------------------------------
+    # readout
+    # ------------------------------------------------------------------------------------------------
+    def _Ts(self, nodes=None):
+        nodes = self._stateNodes if nodes is None else nodes
+        if nodes is None:
+            raise RuntimeError('evolve() the circuit first')
+        B = max(n.data.shape[0] for n in nodes)
+        return [n.data if n.data.shape[0] == B else n.data.expand(B, *n.data.shape[1:]).contiguous() for n in nodes]
+
+    def _create_dmNodes(self, _stateNodes: Optional[List[DenseNode]] = None, reduced_index: Optional[List] = None):
+        nodes = self._stateNodes if _stateNodes is None else _stateNodes
+        dm = DmNodes(nodes, reduced=reduced_index or [])
+        return dm.state_nodes, dm.conj_nodes
+
+    def cal_dmNodes(self, reduced_index: Optional[List] = None):
+        """The un-contracted density operator: n ket-side nodes followed by n conjugated ones. As in the
+        reference (Circuit.py:244 passes reduced_index into another slot) no qubit is traced here."""
+        self._dmNodes = DmNodes(self._stateNodes, reduced=[])
+        return self._dmNodes
+
+    def cal_dm(self, reduced_index: Optional[List] = None, _replicate_require: bool = False):
+        """Dense, un-normalised density matrix of the qubits not in reduced_index (small registers only)."""
+        reduced_index = reduced_index or []
+        if self._dmNodes is None or _replicate_require:
+            self._dmNodes = DmNodes(self._stateNodes, reduced=[])
+        eng = self._engine()
+        keep = [i for i in range(self.qnumber) if i not in reduced_index]
+        dm = eng.dense_rho(self._Ts(), keep=keep).to(self.dtype)
+        self._dm = dm[0] if dm.shape[0] == 1 else dm
+        return self._dm
+
+    def cal_vector(self):
+        if not self.ideal:
+            raise ValueError('Noisy circuit cannot be represented by state vector efficiently.')
+        v = self._engine().dense_vector(self._Ts()).to(self.dtype)
+        self._vector = v[0].reshape(-1, 1) if v.shape[0] == 1 else v.unsqueeze(-1)
+        return self._vector
+
+    def bitstring_probabilities(self, bitstrings, normalize: bool = False) -> tc.Tensor:
+        """<b|rho|b> for a batch of full-register bitstrings (list of lists / strings of 0/1) by one
+        transfer-matrix chain (the product of the reference's conditional probabilities, Circuit.py:297-332)."""
+        bits = [[int(c) for c in b] if isinstance(b, str) else list(b) for b in bitstrings]
+        eng = self._engine()
+        probs = eng.bitstring_probs(self._Ts(), bits)
+        if normalize:
+            probs = probs / eng.chain_value(self._Ts())[0].real
+        return probs
+
+    # ---- sampling (reference :297-467) --------------------------------------------------------------
+    def _conditional_prb(self, _history: List[Union[int, bool]]) -> float:
+        """P(next measured qubit = 1 | history) on the prepared sampling state."""
+        ctx = self._nodes4samples
+        L = ctx['L0']
+        for j, bit in enumerate(_history):
+            L = ctx['eng'].transfer_proj(L, ctx['Ts'][j], int(bit))
+        return self._p1_from_left(L, len(_history))
+
+    def _p1_from_left(self, L, pos):
+        ctx = self._nodes4samples
+        eng, Ts, Rs = ctx['eng'], ctx['Ts'], ctx['R']
+        vals = []
+        for bit in (0, 1):
+            Lb = eng.transfer_proj(L, Ts[pos], bit)
+            vals.append(eng.inner(Lb, Rs[pos + 1])[0].real.item())
+        probs = tc.tensor(vals, dtype=tc.float64) + GLOBAL_MINIMUM
+        if (probs < 0).sum() > 0:
+            raise RuntimeError(f"State is illegal, and your probability distribution is {probs}.")
+        return (probs / probs.sum())[-1].item()
+
+    def _prepare_sampling(self, nodes, measured: List[int]):
+        """Order the measured qubits first is not possible on a chain; instead trace the reduced qubits inside
+        the transfer matrices: sites not in `measured` contribute identity-traced transfer matrices."""
+        eng = self._engine()
+        Ts_all = self._Ts(nodes)
+        assert Ts_all[0].shape[0] == 1, 'sampling works on a single circuit'
+        n = len(Ts_all)
+        if measured != list(range(n)):
+            raise NotImplementedError('sampling of a reduced register is listed as "next" (SURVEY 8f)')
+        # right environments R[k] = trace of sites k..n-1, as [1, l, l'] (c128)
+        R = [None] * (n + 1)
+        R[n] = tc.ones((1, 1, 1), dtype=tc.complex128, device=Ts_all[0].device)
+        for k in range(n - 1, -1, -1):
+            R[k] = eng.transfer_right(R[k + 1], Ts_all[k])
+        self._nodes4samples = {'eng': eng, 'Ts': Ts_all, 'R': R,
+                               'L0': tc.ones((1, 1, 1), dtype=tc.complex128, device=Ts_all[0].device)}
+        self._indices4samples = measured
+
+    def _conditional_batch_sample(self, shots: int, _sampleLength: int, _bool: bool = False,
+                                  _tqdm_disable: bool = False) -> List[List[int]]:
+        """Breadth-first over outcome prefixes: one conditional probability per distinct prefix, shot counts
+        split by Bernoulli draws (reference :344-387). Left environments are carried per prefix group."""
+        dtype = tc.bool if _bool else tc.int
+        sequences = tc.zeros((shots, _sampleLength), dtype=dtype)
+        ctx = self._nodes4samples
+        groups = [(ctx['L0'], 0, shots)]
+        for pos in range(_sampleLength):
+            nxt = []
+            for L, start, length in groups:
+                if length == 0:
+                    continue
+                p1 = self._p1_from_left(L, pos)
+                if p1 < GLOBAL_MINIMUM:
+                    k1 = 0
+                elif p1 > 1 - GLOBAL_MINIMUM:
+                    k1 = length
+                else:
+                    k1 = int(tc.bernoulli(tc.full((length,), p1)).sum())
+                k0 = length - k1
+                sequences[start:start + k1, pos] = True if _bool else 1
+                if pos < _sampleLength - 1:
+                    if k1 > 0:
+                        nxt.append((ctx['eng'].transfer_proj(L, ctx['Ts'][pos], 1), start, k1))
+                    if k0 > 0:
+                        nxt.append((ctx['eng'].transfer_proj(L, ctx['Ts'][pos], 0), start + k1, k0))
+            groups = nxt
+        return sequences.tolist()
+
+    def _conditional_sample(self, shots: int, _sampleLength: int, _tqdm_disable: bool = False) -> List[List[int]]:
+        out = []
+        for _ in range(shots):
+            choices = []
+            for _j in range(_sampleLength):
+                p1 = self._conditional_prb(choices)
+                choices.append(int(tc.multinomial(tc.tensor([1 - p1, p1]), num_samples=1).item()))
+            out.append(choices)
+        return out
+
+    def sample(self, shots: Optional[int] = None, orientation: Optional[List[int]] = None,
+               reduced: Optional[List[int]] = None, sample_string: bool = True, _tqdm_disable: bool = False,
+               _require_sequential_sample: bool = False, _require_bool_result: bool = False,
+               _require_counts: bool = True, _stateNodes4Sample: Optional[List[DenseNode]] = None):
+        """Sample measurement outcomes (orientation per measured qubit: 0 = X, 1 = Y, 2 = Z)."""
+        shots = shots or 1024
+        reduced = reduced or []
+        ori_list = [q for q in range(self.qnumber) if q not in reduced]
+        length = len(ori_list)
+        orientation = orientation or [2] * length
+        if len(orientation) != length:
+            raise ValueError("Length of orientation must match the sample length. Check reduced or unmeasured qubits.")
+        nodes = replicate_nodes(self._stateNodes if _stateNodes4Sample is None else _stateNodes4Sample)
+        for val, cls in [(0, MeasureX), (1, MeasureY)]:
+            idx = [ori_list[i] for i, v in enumerate(orientation) if v == val]
+            if idx:
+                self._add_gate(nodes, 0, idx, cls(dtype=self.dtype, device='cpu'))
+        self._prepare_sampling(nodes, ori_list)
+        if not _tqdm_disable:
+            print('Sample Direction:\n (scheme-' + ''.join(self._projectors_string[v] for v in orientation) + ')')
+        if _require_sequential_sample:
+            bitstrings = self._conditional_sample(shots, length, _tqdm_disable)
+        else:
+            bitstrings = self._conditional_batch_sample(shots, length, _bool=_require_bool_result,
+                                                        _tqdm_disable=_tqdm_disable)
+        if sample_string and not _require_bool_result:
+            bitstrings = [''.join(map(str, b)) for b in bitstrings]
+        self._samples = bitstrings
+        if _require_counts:
+            self._counts = count_item(bitstrings)
+            return self._samples, self._counts
+        return self._samples
+
+    def randomSample(self, measurement_schemes: List[List[int]], shots_per_scheme: int = 1024,
+                     reduced: Optional[List[int]] = None, _tqdm_disable: bool = False,
+                     _require_sequential_sample: bool = False, _require_bool_result: bool = False,
+                     _stateNodes4Sample: Optional[List[DenseNode]] = None):
+        return [
+            self.sample(shots=shots_per_scheme, orientation=scheme, reduced=reduced, sample_string=False,
+                        _tqdm_disable=True, _require_sequential_sample=_require_sequential_sample,
+                        _require_bool_result=_require_bool_result, _require_counts=False,
+                        _stateNodes4Sample=_stateNodes4Sample)
+            for scheme in measurement_schemes
+        ]

@@ -1,0 +1,85 @@
+"""Truncation sweeps of the B200 build (reference MPDOSimulator/TNNOptimizer.py): same function names and
+argument meaning, operating in place on a list of dense site nodes. Every sweep step is a short sequence
+of CUDA launches (see _engine/steps.py); there is no CPU path."""
+from typing import List, Optional
+
+from . import _engine
+from ._node import DenseNode
+
+__all__ = ['qr_left2right', 'svd_left2right', 'svd_right2left', 'svdKappa_left2right', 'bondTruncate',
+           'checkConnectivity']
+
+
+def checkConnectivity(_qubits: List[DenseNode]):
+    """True when every neighbouring pair shares a bond (tn.check_connected, TNNOptimizer.py:51-61)."""
+    if len(_qubits) <= 1:
+        return True
+    return all(q.has_right for q in _qubits[:-1])
+
+
+def _validate_qubit_list(qubits, func_name: str):
+    if not isinstance(qubits, list):
+        raise TypeError(f'`{func_name}` expects a list of qubit nodes, got {type(qubits).__name__}')
+
+
+def _engine_of(qubits):
+    """Engine for the state's dtype; also brings every site to the common batch size (a parameter-sweep batch
+    starts on the sites its batched gates touched, the sweeps need it everywhere)."""
+    B = max(q.data.shape[0] for q in qubits)
+    for q in qubits:
+        if q.data.shape[0] != B:
+            q.data = q.data.expand(B, *q.data.shape[1:]).contiguous()
+    return _engine.engine_for(qubits[0].data.dtype)
+
+
+def bondTruncate(_qubits: List[DenseNode], max_singular_values: Optional[int] = None,
+                 max_truncation_err: Optional[float] = None, regularization: bool = False):
+    """QR sweep left-to-right, then SVD truncation right-to-left (TNNOptimizer.py:72-84)."""
+    if max_singular_values is None and max_truncation_err is None and not regularization:
+        return None
+    qr_left2right(_qubits)
+    svd_right2left(_qubits, max_singular_values=max_singular_values, max_truncation_err=max_truncation_err)
+
+
+def qr_left2right(_qubits: List[DenseNode]):
+    """T_i = Q R, T_i <- Q, T_{i+1} <- R T_{i+1} for i = 0..n-2 (TNNOptimizer.py:87-108)."""
+    _validate_qubit_list(_qubits, "qr_left2right")
+    eng = _engine_of(_qubits)
+    for i in range(len(_qubits) - 1):
+        if not _qubits[i].has_right:
+            raise ValueError(f'Axis name bond_{i}_{i + 1} not found')  # the reference indexes it unconditionally
+        _qubits[i].data, _qubits[i + 1].data = eng.qr_step(_qubits[i].data, _qubits[i + 1].data)
+
+
+def svd_right2left(_qubits: List[DenseNode], max_singular_values: Optional[int] = None,
+                   max_truncation_err: Optional[float] = None):
+    """Two-site SVD truncation for idx = n-1..1, sqrt(S) on both sides (TNNOptimizer.py:111-134). The left
+    neighbour is an isometry after qr_left2right, so only T_idx is decomposed (SVD(Q X) = Q SVD(X))."""
+    _validate_qubit_list(_qubits, "svd_right2left")
+    eng = _engine_of(_qubits)
+    discarded = []
+    for idx in range(len(_qubits) - 1, 0, -1):
+        left, right = _qubits[idx - 1], _qubits[idx]
+        left.data, right.data, d = eng.bond_svd_step(left.data, right.data, max_singular_values, max_truncation_err)
+        discarded.append(d)
+    return discarded
+
+
+def svd_left2right(_qubits: List[DenseNode], max_singular_values: int, max_truncation_err: Optional[float] = None):
+    """Never called by the reference (dead code, TNNOptimizer.py:137-161); kept for API completeness."""
+    raise NotImplementedError('svd_left2right is dead code in the reference and is not part of the B200 build')
+
+
+def svdKappa_left2right(_qubits: List[DenseNode], max_singular_values: Optional[int] = None,
+                        max_truncation_err: Optional[float] = None):
+    """Inner-index truncation T <- U S per site (TNNOptimizer.py:164-197)."""
+    if max_singular_values is None and max_truncation_err is None:
+        return None
+    _validate_qubit_list(_qubits, "svdKappa_left2right")
+    eng = _engine_of(_qubits)
+    for q in _qubits:
+        if max_singular_values is not None and (not q.has_inner or q.data.shape[3] <= max_singular_values):
+            continue
+        if not q.has_inner:
+            raise ValueError(f'Axis name I_{q.index} not found')
+        q.data, _ = eng.kappa_truncate(q.data, max_singular_values, max_truncation_err)

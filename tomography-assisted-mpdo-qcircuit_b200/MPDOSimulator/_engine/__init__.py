@@ -6,3 +6,26 @@ def default_prims():
     """The product back end. Raises when libmpdo_b200.so or a CUDA device is missing (no CPU fallback)."""
     from .prims import CudaPrims
     return CudaPrims()
+
+
+_PRIMS = None          # process-wide device back end, created on first use
+_TEST_PRIMS = None     # test hook only (tests/cpu_prims.py); never set by product code
+_ENGINES = {}
+
+
+def prims():
+    global _PRIMS
+    if _TEST_PRIMS is not None:
+        return _TEST_PRIMS
+    if _PRIMS is None:
+        _PRIMS = default_prims()
+    return _PRIMS
+
+
+def engine_for(dtype):
+    """Engine (kernel sequences of the update path) for a circuit dtype."""
+    p = prims()
+    key = (id(p), dtype)
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(p, dtype)
+    return _ENGINES[key]

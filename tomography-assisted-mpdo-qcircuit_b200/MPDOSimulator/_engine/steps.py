@@ -204,8 +204,8 @@ class Engine:
             k = self._keep(s, None, max_err, False)
             # U_L = Q . Uh_^h  ->  UL rows: sqrt(s_j) conj(U_L[:, j])
             XU = torch.empty((Bn, k, ncol), dtype=C128, device=dev)
-            p.contract(p.rowscale(Uh_, s, k, 0.5, 0.0, 0, C128), (1, 1, 1), Xs.permute(0, 2, 1), (1, 1, 1), XU,
-                       (1, 1, 1), conjB=True)                     # sqrt(s) Uh_ Xs^*... see note below
+            # conj(U_L[i,j]) = sum_{c,d} Uh_[j,c] Xs[c,d] conj(Alast[i,d])
+            p.contract(p.rowscale(Uh_, s, k, 0.5, 0.0, 0, C128), (1, 1, 1), Xs, (1, 1, 1), XU, (1, 1, 1))
             UL = torch.empty((Bn, k, nrow), dtype=C128, device=dev)
             p.contract(XU, (1, 1, 1), Alast.permute(0, 2, 1), (1, 1, 1), UL, (1, 1, 1), conjB=True)
             Zc = p.rowscale(Wh_, s, k, 0.5, 0.0, 0, C128 if F_hi is not None else self.dtype).reshape(Bn, k, 2, K, y)
@@ -365,6 +365,27 @@ class Engine:
             L = self.transfer(L, T, None if Tcs is None else Tcs[k], ops.get(k))
         return L.reshape(Bn)
 
+    def chain_overlap(self, Ts0, Ts1):
+        """Tr(rho_0 rho_1) of two un-normalised MPDOs on the same register -> [B] complex128 (O(chi^5))."""
+        p = self.p
+        Bn = Ts0[0].shape[0]
+        dev = Ts0[0].device
+        E = torch.ones((Bn, 1, 1, 1, 1), dtype=C128, device=dev)     # [b, l0, l0', l1, l1']
+        for A, T1 in zip(Ts0, Ts1):
+            _, l0, _, a0, r0 = A.shape
+            _, l1, _, a1, r1 = T1.shape
+            X1 = torch.empty((Bn, l0, l1, l1, 2, a0, r0), dtype=C128, device=dev)
+            p.contract(E.permute(0, 2, 3, 4, 1), (1, 3, 1), A, (1, 1, 3), X1, (1, 3, 3))
+            X2 = torch.empty((Bn, l1, l1, 2, r0, 2, r0), dtype=C128, device=dev)
+            p.contract(X1.permute(0, 2, 3, 4, 6, 1, 5), (1, 4, 2), A.permute(0, 1, 3, 2, 4), (1, 2, 2), X2, (1, 4, 2),
+                       conjB=True)
+            X3 = torch.empty((Bn, l1, 2, r0, r0, a1, r1), dtype=C128, device=dev)
+            p.contract(X2.permute(0, 2, 3, 4, 6, 1, 5), (1, 4, 2), T1, (1, 2, 2), X3, (1, 4, 2))
+            En = torch.empty((Bn, r0, r0, r1, r1), dtype=C128, device=dev)
+            p.contract(X3.permute(0, 3, 4, 6, 1, 2, 5), (1, 3, 3), T1, (1, 3, 1), En, (1, 3, 1), conjB=True)
+            E = En
+        return E.reshape(Bn)
+
     def bitstring_probs(self, Ts, bits):
         """<b|rho|b> for bitstrings bits [NB, n] (0/1 ints) of one circuit (B = 1) -> [NB] float64."""
         bits = torch.as_tensor(bits).reshape(-1, len(Ts))
@@ -374,26 +395,52 @@ class Engine:
             L = self.transfer_proj(L, T, bits[:, k])
         return L.reshape(nb).real
 
-    def dense_rho(self, Ts):
-        """Dense un-normalised rho [B, 2^n, 2^n] (small n only)."""
+    def transfer_right(self, R, T, op=None):
+        """R [B,r,r'] (c128) -> R'[l,l'] = sum (O.T)[l,s',a,r] R[r,r'] conj(T[l',s',a,r'])."""
+        p = self.p
+        Bn, l, _, a, r = T.shape
+        Tk = T if op is None else p.absorb_1q(T.contiguous(), op.reshape(-1, 2, 2, 1).to(T.dtype).contiguous())
+        X = torch.empty((Bn, l, 2, a, R.shape[2]), dtype=C128, device=T.device)
+        p.contract(Tk, (1, 3, 1), R, (1, 1, 1), X, (1, 3, 1))
+        Rn = torch.empty((Bn, l, l), dtype=C128, device=T.device)
+        p.contract(X, (1, 1, 3), T.permute(0, 2, 3, 4, 1), (1, 3, 1), Rn, (1, 1, 1), conjB=True)
+        return Rn
+
+    def inner(self, L, R):
+        """sum_{r,r'} L[b,r,r'] R[b,r,r'] -> [B] complex128 (closing a left and a right environment)."""
+        Bn = L.shape[0]
+        out = torch.empty((Bn, 1, 1), dtype=C128, device=L.device)
+        self.p.contract(L.reshape(Bn, 1, -1), (1, 1, 1), R.reshape(Bn, -1, 1), (1, 1, 1), out, (1, 1, 1))
+        return out.reshape(Bn)
+
+    def dense_rho(self, Ts, keep=None):
+        """Dense un-normalised (reduced) rho [B, 2^m, 2^m] over the sites in `keep` (default all; small m only)."""
         p = self.p
         Bn = Ts[0].shape[0]
         n = len(Ts)
+        keep = list(range(n)) if keep is None else list(keep)
         Rm = torch.ones((Bn, 1, 1, 1), dtype=C128, device=Ts[0].device)  # [B, P, l, l']
-        for T in Ts:
+        for k, T in enumerate(Ts):
             _, l, _, a, r = T.shape
             P = Rm.shape[1]
             # Y[b,P,l',s,a,r] = sum_l R[b,P,l,l'] T[b,l,s,a,r]
             Y = torch.empty((Bn, P, l, 2, a, r), dtype=C128, device=T.device)
             p.contract(Rm.permute(0, 1, 3, 2), (1, 2, 1), T, (1, 1, 3), Y.reshape(Bn, P, l, 2 * a * r), (1, 2, 1))
-            # R'[b,P,s,s',r,r'] = sum_{l',a} Y[b,P,l',s,a,r] conj(T[b,l',s',a,r'])
-            Rn = torch.empty((Bn, P, 2, 2, r, r), dtype=C128, device=T.device)
-            p.contract(Y.permute(0, 1, 3, 5, 2, 4), (1, 3, 2), T.permute(0, 1, 3, 2, 4), (1, 2, 2),
-                       Rn.permute(0, 1, 2, 4, 3, 5), (1, 3, 2), conjB=True)
-            Rm = Rn.reshape(Bn, P * 4, r, r)
-        rho = Rm.reshape([Bn] + [2, 2] * n)
-        perm = [0] + [1 + 2 * i for i in range(n)] + [2 + 2 * i for i in range(n)]
-        return rho.permute(perm).reshape(Bn, 2 ** n, 2 ** n)
+            if k in keep:
+                # R'[b,P,s,s',r,r'] = sum_{l',a} Y[b,P,l',s,a,r] conj(T[b,l',s',a,r'])
+                Rn = torch.empty((Bn, P, 2, 2, r, r), dtype=C128, device=T.device)
+                p.contract(Y.permute(0, 1, 3, 5, 2, 4), (1, 3, 2), T.permute(0, 1, 3, 2, 4), (1, 2, 2),
+                           Rn.permute(0, 1, 2, 4, 3, 5), (1, 3, 2), conjB=True)
+                Rm = Rn.reshape(Bn, P * 4, r, r)
+            else:
+                # R'[b,P,r,r'] = sum_{l',s,a} Y[b,P,l',s,a,r] conj(T[b,l',s,a,r'])
+                Rn = torch.empty((Bn, P, r, r), dtype=C128, device=T.device)
+                p.contract(Y.permute(0, 1, 5, 2, 3, 4), (1, 2, 3), T, (1, 3, 1), Rn, (1, 2, 1), conjB=True)
+                Rm = Rn
+        m = len(keep)
+        rho = Rm.reshape([Bn] + [2, 2] * m)
+        perm = [0] + [1 + 2 * i for i in range(m)] + [2 + 2 * i for i in range(m)]
+        return rho.permute(perm).reshape(Bn, 2 ** m, 2 ** m)
 
     def dense_vector(self, Ts):
         """Dense state vector [B, 2^n] of an ideal circuit (inner dims all 1)."""
