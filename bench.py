@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py - noisy two-qubit-gate updates/sec of the MPDO update path on B200.
+
+Workload (BASELINE.json configs[1], SURVEY 8d "cfg2"): 20-qubit brickwork, complex64, chi = 64, kappa = 4,
+noiseType = 'realNoise' with the tomography chi-matrix czDefault.mat on every bond. Layer d =
+[u3 on every qubit ; rzz(theta, q, q+1) on bonds q = d mod 2 ; truncate()], and every rzz is rewritten by the
+reference API into cx.rz.cx = two chi-matrix CZ updates (K = 16 Kraus terms each) with no truncation in
+between. Angles come from torch.Generator().manual_seed(1234 + circuit_id).
+
+A "step" is one such layer on one circuit per GPU: W warm-up layers bring the bonds to chi, then exactly K
+layers are timed with CUDA events between barrier+synchronize pairs (max over ranks). A single MPDO sweep is
+sequential and does not shard, so --gpus N runs N independent circuits (replicas; circuit_id = rank), NCCL
+only gathers the per-circuit readout at the end of the timed region.
+
+  value  : noisy 2q updates / s, state resident in HBM when the clock starts
+  e2e    : same layers through the public API from pinned HOST buffers (H2D of the state, evolve, D2H of the
+           state) inside the timed region
+  roofline / cpu_baseline: see DESIGN.md section 5.
+
+`--impl reference` times the reference's own formulation on the host cores: the oracle in reference mode
+(torch CPU, all threads) on a bounded sample of the same workload - one rzz (two chi-matrix CZ updates) on a
+steady-state three-site window plus the QR / chi-SVD / kappa-SVD steps that touch that pair.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'tomography-assisted-mpdo-qcircuit_b200')
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+N_QUBITS, CHI, KAPPA, DEPTH = 20, 64, 4, 20
+METRIC = 'noisy_2q_gate_updates_per_sec'
+UNIT = 'updates/s'
+WORKLOAD = 'cfg2: 20q U3+RZZ brickwork depth 20, realNoise czDefault chi-matrix (K=16), chi=64, kappa=4, complex64'
+
+
+def chi_file():
+    return os.path.join(PKG, 'MPDOSimulator', 'chi', 'czDefault.mat')
+
+
+def layer_angles(circuit_id, depth=DEPTH, n=N_QUBITS):
+    """Layer-major, qubit-minor Python floats: 3 per u3, then one per rzz of the layer."""
+    g = torch.Generator().manual_seed(1234 + circuit_id)
+    out = []
+    for d in range(depth):
+        u = [(torch.rand(3, generator=g, dtype=torch.float64) * 2 * math.pi).tolist() for _ in range(n)]
+        z = [float(torch.rand(1, generator=g, dtype=torch.float64) * 2 * math.pi) for _ in range(d % 2, n - 1, 2)]
+        out.append((u, z))
+    return out
+
+
+def add_layer(circ, d, angles, n=N_QUBITS):
+    u, z = angles[d]
+    for q in range(n):
+        circ.u3(u[q][0], u[q][1], u[q][2], [q])
+    for i, q in enumerate(range(d % 2, n - 1, 2)):
+        circ.rzz(z[i], q, q + 1)
+    circ.truncate()
+    return 2 * len(z)   # noisy 2q updates in this layer
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.FIELDS}', '--format=csv,noheader,nounits',
+                 '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle in reference mode on a bounded sample
+# ---------------------------------------------------------------------------------------------------
+def cpu_sample(repeats=1, threads=None):
+    """One rzz (= 2 chi-matrix CZ updates) on sites (1, 2) of a four-site steady-state window with Gaussian
+    tensors (re, im ~ N(0,1)/sqrt(2 chi kappa), seed 7; SURVEY 8d micro-benchmark) followed by the truncate
+    sweep of the window, oracle in reference mode (randomized SVD branch as in decompositions.py:112-115).
+    Returns (updates, seconds per repeat list, cores)."""
+    from oracle.mpdo_oracle import OracleCircuit
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    files = {'CZ': {'12': chi_file()}, 'CP': {}}
+    times = []
+    for rep in range(repeats):
+        oc = OracleCircuit(4, ideal=False, noiseType='realNoise', chiFileDict=files, chi=CHI, kappa=KAPPA,
+                           chip='best', dtype=torch.complex64, svd_mode='reference')
+        oc.rzz(0.7 + 0.1 * rep, 1, 2)
+        oc.truncate()
+        g = torch.Generator().manual_seed(7)
+        scale = 1.0 / math.sqrt(2 * CHI * KAPPA)
+
+        def gauss(l, r):
+            return torch.complex(torch.randn(l, 2, KAPPA, r, generator=g), torch.randn(l, 2, KAPPA, r, generator=g)) * scale
+
+        oc.T = [gauss(1, CHI), gauss(CHI, CHI), gauss(CHI, CHI), gauss(CHI, 1)]
+        oc.bond = [True, True, True]
+        oc.inner = [True] * 4
+        t0 = time.perf_counter()
+        oc.run_layers()
+        times.append(time.perf_counter() - t0)
+    return 2, times, threads
+
+
+def reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    for _ in range(args.warmup):
+        pass  # the sample is deterministic CPU work; warm-up repeats would only lengthen the run
+    updates, times, cores = cpu_sample(repeats=max(1, args.steps))
+    total = sum(times)
+    value = updates * len(times) / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
+        'config': {'workload': WORKLOAD, 'chi': CHI, 'kappa': KAPPA},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': 'oracle (reference mode) on one rzz = 2 chi-matrix CZ updates + the truncate '
+                                   'sweep of a 4-site steady-state Gaussian window, per step'},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+class TimedPrims:
+    """Wraps the device primitives to time the dominant kernel class (large contractions) with CUDA events on
+    the launching stream, inside the timed region."""
+
+    def __init__(self, prims, min_flops=2e9):
+        self.p, self.min_flops, self.records, self.enabled = prims, min_flops, [], False
+
+    def __getattr__(self, name):
+        return getattr(self.p, name)
+
+    def contract(self, A, ra, B, rb, Cv, rc, **kw):
+        if not self.enabled:
+            return self.p.contract(A, ra, B, rb, Cv, rc, **kw)
+        nb, ni, nk = ra
+        M = math.prod(A.shape[nb:nb + ni])
+        K = math.prod(A.shape[nb + ni:])
+        N = math.prod(B.shape[rb[0] + rb[1]:])
+        batch = math.prod(A.shape[:nb])
+        flops = 8.0 * M * N * K * batch
+        if flops < self.min_flops:
+            return self.p.contract(A, ra, B, rb, Cv, rc, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = self.p.contract(A, ra, B, rb, Cv, rc, **kw)
+        e1.record()
+        csize = lambda t: 8 if t.dtype == torch.complex64 else 16
+        byts = batch * (M * K * csize(A) + K * N * csize(B) + M * N * csize(Cv))
+        fp32 = A.dtype == B.dtype == Cv.dtype == torch.complex64 and not kw.get('acc64')
+        self.records.append((e0, e1, flops, byts, fp32, (M, N, K, batch)))
+        return out
+
+    def summary(self):
+        torch.cuda.synchronize()
+        rows = [(e0.elapsed_time(e1) * 1e-3, fl, by, fp32, shp) for e0, e1, fl, by, fp32, shp in self.records]
+        return rows
+
+
+def b200_arm(args):
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = f'cuda:{local}'
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+
+    import MPDOSimulator as Simulator
+    from MPDOSimulator import _engine
+    base = _engine.prims()
+    timed = TimedPrims(base)
+    _engine._PRIMS = timed
+    _engine._ENGINES.clear()
+
+    n, K, W = N_QUBITS, args.steps, args.warmup
+    assert W >= 3, 'timing rules: at least 3 warm-up steps'
+    files = {'CZ': {f'{i}{i + 1}': chi_file() for i in range(n - 1)}, 'CP': {}}
+    angles = layer_angles(rank, depth=max(DEPTH, W + 2 * K))
+
+    def layer_circuit(d):
+        c = Simulator.TensorCircuit(qn=n, ideal=False, noiseType='realNoise', chiFileDict=files, chi=CHI,
+                                    kappa=KAPPA, chip='best', dtype=torch.complex64, device=dev)
+        upd = add_layer(c, d, angles)
+        return c, upd
+
+    circuits = [layer_circuit(d) for d in range(W + 2 * K)]
+    state = Simulator.Tools.create_ket0Series(n, dtype=torch.complex64, device='cpu')
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for d in range(W):
+        circuits[d][0].evolve(state)
+    barrier()
+
+    # ---- timed region: device-resident state -----------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    timed.enabled = True
+    launches0 = base.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    updates = 0
+    for d in range(W, W + K):
+        flush.zero_()
+        c, upd = circuits[d]
+        c.evolve(state)
+        updates += upd
+    if world > 1:   # the one exchange step of the path: gather the per-circuit readout
+        readout = circuits[W + K - 1][0].bitstring_probabilities(['0' * n]).to(torch.float64).reshape(1)
+        gathered = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(gathered, readout)
+    ev1.record()
+    barrier()
+    timed.enabled = False
+    launches = base.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    secs = ev0.elapsed_time(ev1) * 1e-3
+    kern_rows = timed.summary()
+    bond_dims = [int(s.data.shape[4]) for s in state[:-1]]
+
+    # ---- e2e: host buffers in, host buffers out, every step -------------------------------------------
+    host = [s.data.cpu().pin_memory() for s in state]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d = d2h = 0
+    barrier()
+    e0.record()
+    e2e_updates = 0
+    for d in range(W + K, W + 2 * K):
+        flush.zero_()
+        for s, h in zip(state, host):
+            s.data = h.to(dev, non_blocking=True)
+            h2d += h.numel() * h.element_size()
+        c, upd = circuits[d]
+        c.evolve(state)
+        e2e_updates += upd
+        host = []
+        for s in state:
+            hb = torch.empty(s.data.shape, dtype=s.data.dtype, pin_memory=True)
+            hb.copy_(s.data, non_blocking=True)
+            host.append(hb)
+            d2h += hb.numel() * hb.element_size()
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    barrier()
+    e2e_secs = e0.elapsed_time(e1) * 1e-3
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.item()
+
+    secs, e2e_secs = max_over_ranks(secs), max_over_ranks(e2e_secs)
+    tot_updates, tot_e2e_updates = sum_over_ranks(updates), sum_over_ranks(e2e_updates)
+    tot_launches = sum_over_ranks(launches)
+
+    if rank == 0:
+        peaks = {}
+        pk = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+        if os.path.exists(pk):
+            peaks = json.load(open(pk))
+        peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
+        peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.4 PFLOP/s'
+        tot_t = sum(r[0] for r in kern_rows) or 1e-30
+        tot_f = sum(r[1] for r in kern_rows)
+        big = max(kern_rows, key=lambda r: r[1]) if kern_rows else None
+        roof = {
+            'bound': 'tensor', 'kernel': 'contract_kernel (batched complex contraction, FP32 FFMA / FP64 DFMA SIMT tiles)',
+            'achieved': tot_f / tot_t / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tot_f / tot_t / 1e12 / peak_tf,
+            'traffic': None, 'peak_source': peak_src,
+            'launches_timed': len(kern_rows), 'kernel_seconds': tot_t, 'share_of_step': tot_t / secs,
+            'largest_launch': None if big is None else {'M_N_K_batch': big[4], 'ms': big[0] * 1e3,
+                                                        'TFLOP/s': big[1] / big[0] / 1e12, 'fp32': big[3]},
+            'note': 'algorithmic flops = 8*M*N*K per complex contraction (SURVEY 8d); launches >= 2 GFLOP timed with '
+                    'CUDA events on the launching stream inside the timed region; the denominator is the dense bf16 '
+                    'tensor peak although the kernel must deliver fp32/fp64-accurate complex arithmetic',
+        }
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            upd, times, cores = cpu_sample(repeats=1)
+            cpu = {'value': upd / times[0], 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                   'sample': 'oracle (reference mode) on one rzz = 2 chi-matrix CZ updates + the truncate sweep of '
+                             'a 4-site steady-state Gaussian window (%.1f s)' % times[0]}
+        line = {
+            'metric': METRIC, 'value': tot_updates / secs, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': 1e3 * secs / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'c64', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD, 'chi': CHI, 'kappa': KAPPA, 'qubits': n,
+                       'step': 'one brickwork layer (20 u3 + 9-10 rzz = 18-20 chi-matrix CZ updates + truncate) per GPU',
+                       'parallelism': f'replicas x{world} (one circuit per GPU)',
+                       'l2': 'flushed between steps (256 MB write); per-pair transients are 537 MB > L2',
+                       'bond_dims_after_timed_region': bond_dims},
+            'e2e': {'value': tot_e2e_updates / e2e_secs, 'unit': UNIT, 'h2d_bytes_per_step': h2d // K,
+                    'd2h_bytes_per_step': d2h // K, 'ms_per_step': 1e3 * e2e_secs / K},
+            'gpu_launches': int(tot_launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == '__main__':
+    main()

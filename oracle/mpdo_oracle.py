@@ -421,6 +421,11 @@ class OracleCircuit:
         self.T = [s.to(self.dtype).reshape(1, 2, 1, 1) for s in state]
         self.bond = [False] * (self.qn - 1)
         self.inner = [False] * self.qn
+        return self.run_layers()
+
+    def run_layers(self):
+        """The layer loop of evolve on the current self.T / self.bond / self.inner (lets a caller start from a
+        prepared mid-circuit window)."""
         for layer in self.layers:
             if layer[0] == 'truncate':
                 if self._connected():

@@ -123,6 +123,30 @@ class Engine:
         Uh_, s, Wh_ = self.p.svd_rows(Lh, self.jacobi_tol)
         return Wh_, s, Uh_
 
+    def svd_wide(self, M, roles):
+        """Truncatable SVD of a wide view M [b | rows | cols] = U diag(s) Vh without forming Vh:
+        returns (Mlast, sv, squared, right, left) where sv [B,n] holds the singular values (their squares if
+        `squared`), right(k, dtype) is the [B,k,n] core with sqrt(S_k) Vh_k = right . Mlast, and
+        left(k, dtype)[j, i] = sqrt(s_j) conj(U[i, j]). One-pass mode reads both cores straight off the Gram
+        eigen-decomposition; two-pass mode orthogonalises twice and runs the Jacobi SVD on the small core."""
+        p = self.p
+        if self.npass == 1:
+            G = self._gram_rows(M, roles)
+            lam, Uh = p.eigh_psd(G, self.jacobi_tol)
+            right = lambda k, dt: p.rowscale(Uh, lam, k, -0.25, self.null_tol, 0, dt)
+            left = lambda k, dt: p.rowscale(Uh, lam, k, 0.25, self.null_tol, 0, dt)
+            return M, lam, True, right, left
+        Mlast, F, Lh = self.orth_rows(M, roles)
+        Uh_L, s, Wh_L = self._svd_core(Lh)
+
+        def right(k, dt):
+            WF = torch.empty((F.shape[0], k, F.shape[2]), dtype=dt, device=F.device)
+            p.contract(p.rowscale(Wh_L, s, k, 0.5, 0.0, 0, C128), (1, 1, 1), F, (1, 1, 1), WF, (1, 1, 1))
+            return WF
+
+        left = lambda k, dt: p.rowscale(Uh_L, s, k, 0.5, 0.0, 0, dt)
+        return Mlast, s, False, right, left
+
     def _keep(self, s, cap, max_err, relative, squared=False):
         """Apply the reference rank rule; returns the common (batch-max) kept rank. s is zero-tailed in place."""
         n = s.shape[1]
@@ -188,15 +212,11 @@ class Engine:
         Cv = Cm.reshape(Bn, 2 * x, 2 * K * y)
         nrow, ncol = 2 * x, 2 * K * y
         if nrow <= ncol:
-            Mlast, F, Lh = self.orth_rows(Cv, (1, 1, 1))
-            Uh_L, s, Wh_L = self._svd_core(Lh)                   # core = U_L diag(s) Wh_L . (F . Mlast)
-            k = self._keep(s, None, max_err, False)
-            # Tlo'[(x,p0), j] = U_L[(x,p0), j] sqrt(s_j) -> conj of rowscale(Uh_L)
-            UL = p.rowscale(Uh_L, s, k, 0.5, 0.0, 0, C128)       # [B,k,(x,p0)], entries sqrt(s_j) conj(U)[.,j]
-            WF = torch.empty((Bn, k, nrow), dtype=C128, device=dev)
-            p.contract(p.rowscale(Wh_L, s, k, 0.5, 0.0, 0, C128), (1, 1, 1), F, (1, 1, 1), WF, (1, 1, 1))
+            Mlast, sv, sq, right, left = self.svd_wide(Cv, (1, 1, 1))
+            k = self._keep(sv, None, max_err, False, squared=sq)
+            UL = left(k, C128)                                   # [B,k,(x,p0)] = sqrt(s_j) conj(U[(x,p0), j])
             Zc = torch.empty((Bn, k, 2, K, y), dtype=C128 if F_hi is not None else self.dtype, device=dev)
-            p.contract(WF, (1, 1, 1), Mlast, (1, 1, 1), Zc.reshape(Bn, k, ncol), (1, 1, 1))
+            p.contract(right(k, C128), (1, 1, 1), Mlast, (1, 1, 1), Zc.reshape(Bn, k, ncol), (1, 1, 1))
         else:
             # tall core (rare: tiny right factor): decompose the column side instead
             Alast, Xs, R = self.orth_cols(Cv, (1, 1, 1))         # Cv = (Alast Xs^h) R, R [B,ncol,ncol]
@@ -258,17 +278,14 @@ class Engine:
         values (and optionally to the relative error max_err); returns (Tl.U sqrt(S), sqrt(S) Vh, s_discarded)."""
         p = self.p
         Bn, l, _, a, r = Tr.shape
-        Mlast, F, Lh = self.orth_rows(Tr, (1, 1, 3))
-        Uh_L, s, Wh_L = self._svd_core(Lh)
-        k = self._keep(s, chi, max_err, True)
-        disc = s[:, k:].clone()
-        # Tr' = sqrt(S_k) Wh_L[:k] F Mlast
-        WF = torch.empty((Bn, k, l), dtype=self.dtype, device=Tr.device)
-        p.contract(p.rowscale(Wh_L, s, k, 0.5, 0.0, 0, C128), (1, 1, 1), F, (1, 1, 1), WF, (1, 1, 1))
+        Mlast, sv, sq, right, left = self.svd_wide(Tr, (1, 1, 3))
+        k = self._keep(sv, chi, max_err, True, squared=sq)
+        disc = sv[:, k:].clamp_min(0).sqrt() if sq else sv[:, k:].clone()
+        # Tr' = sqrt(S_k) Vh_k = right . Mlast
         Tr_n = self._empty((Bn, k, 2, a, r), Tr)
-        p.contract(WF, (1, 1, 1), Mlast, (1, 1, 3), Tr_n, (1, 1, 3))
-        # Tl' = Tl . U_L[:, :k] sqrt(S_k):  U_L[r,j] sqrt(s_j) = conj(UL[j,r])
-        UL = p.rowscale(Uh_L, s, k, 0.5, 0.0, 0, self.dtype)
+        p.contract(right(k, self.dtype), (1, 1, 1), Mlast, (1, 1, 3), Tr_n, (1, 1, 3))
+        # Tl' = Tl . U[:, :k] sqrt(S_k):  U[r,j] sqrt(s_j) = conj(UL[j,r])
+        UL = left(k, self.dtype)
         Tl_n = self._empty(tuple(Tl.shape[:4]) + (k,), Tl)
         p.contract(Tl, (1, 3, 1), UL.permute(0, 2, 1), (1, 1, 1), Tl_n, (1, 3, 1), conjB=True)
         return Tl_n, Tr_n, disc
