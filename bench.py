@@ -216,7 +216,7 @@ def b200_arm(args):
 
     import MPDOSimulator as Simulator
     from MPDOSimulator import _engine
-    base = _engine.prims()
+    base = _engine.get_prims()
     timed = TimedPrims(base)
     _engine._PRIMS = timed
     _engine._ENGINES.clear()
@@ -244,6 +244,18 @@ def b200_arm(args):
     for d in range(W):
         circuits[d][0].evolve(state)
     barrier()
+
+    if args.profile:   # per-kernel device-time table of one steady-state layer (not a benchmark number)
+        from torch.profiler import ProfilerActivity, profile
+        t0 = time.perf_counter()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            circuits[W][0].evolve(state)
+            torch.cuda.synchronize()
+        wall = time.perf_counter() - t0
+        with open(args.profile, 'w') as f:
+            f.write(f'one layer under the profiler: wall {wall:.3f} s\n')
+            f.write(prof.key_averages().table(sort_by='cuda_time_total', row_limit=25, max_name_column_width=90))
+        return
 
     # ---- timed region: device-resident state -----------------------------------------------------
     sampler = ClockSampler(local)
@@ -369,6 +381,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile', default=None, help='write a per-kernel time table of one steady-state step here')
     args = ap.parse_args()
     if args.impl == 'reference':
         reference_arm(args)

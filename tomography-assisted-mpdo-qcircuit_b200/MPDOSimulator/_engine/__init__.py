@@ -13,7 +13,7 @@ _TEST_PRIMS = None     # test hook only (tests/cpu_prims.py); never set by produ
 _ENGINES = {}
 
 
-def prims():
+def get_prims():
     global _PRIMS
     if _TEST_PRIMS is not None:
         return _TEST_PRIMS
@@ -24,7 +24,7 @@ def prims():
 
 def engine_for(dtype):
     """Engine (kernel sequences of the update path) for a circuit dtype."""
-    p = prims()
+    p = get_prims()
     key = (id(p), dtype)
     if key not in _ENGINES:
         _ENGINES[key] = Engine(p, dtype)

@@ -33,6 +33,7 @@ class Engine:
         self.floor_tol = 1e-13   # first-pass floor of the two-pass scheme
         self.jacobi_tol = 1e-15
         self.stats = {'discarded': []}
+        self._omega = {}         # fixed start blocks of the subspace iteration, per (n, block, device)
 
     # ------------------------------------------------------------------------------------------
     # helpers
@@ -293,12 +294,72 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # R3: inner-index (kappa) truncation                 TNNOptimizer.py:164-197
     # ------------------------------------------------------------------------------------------
+    def eigh_topk(self, G, k, max_iter=40):
+        """Leading k eigenpairs of Hermitian PSD G [B,n,n] (complex128) by block subspace iteration with
+        Rayleigh-Ritz, iterated until the residuals |G v - theta v| of the k kept pairs are at rounding level
+        (this is an exact solver run to convergence, unlike the reference's three un-orthonormalised power
+        steps; it replaces the full Jacobi decomposition when k << n). Returns (theta [B,k], Vt [B,k,n]) with
+        Vt[j,:] the components of eigenvector j (not conjugated), or None when it does not converge."""
+        p = self.p
+        Bn, n, _ = G.shape
+        blk = min(n, max(2 * k, k + 28))
+        tol = 1e-10 if self.f32 else 1e-12
+        key = (n, blk, str(G.device))
+        if key not in self._omega:
+            g = torch.Generator().manual_seed(20261017)
+            om = torch.complex(torch.randn(blk, n, generator=g, dtype=torch.float64),
+                               torch.randn(blk, n, generator=g, dtype=torch.float64))
+            self._omega[key] = om.to(G.device)
+        Yr = self._omega[key].unsqueeze(0).expand(Bn, blk, n)
+        Gt = G.permute(0, 2, 1)
+        Zr = torch.empty((Bn, blk, n), dtype=C128, device=G.device)
+        p.contract(Yr, (1, 1, 1), Gt, (1, 1, 1), Zr, (1, 1, 1))
+        for it in range(max_iter):
+            # orthonormalise the rows of Zr
+            H = self._gram_rows(Zr, (1, 1, 1))
+            lam, Uh = p.eigh_psd(H, self.jacobi_tol)
+            Yr = torch.empty((Bn, blk, n), dtype=C128, device=G.device)
+            p.contract(p.rowscale(Uh, lam, blk, -0.5, self.null_tol, 0, C128), (1, 1, 1), Zr, (1, 1, 1), Yr, (1, 1, 1))
+            Zr = torch.empty((Bn, blk, n), dtype=C128, device=G.device)
+            p.contract(Yr, (1, 1, 1), Gt, (1, 1, 1), Zr, (1, 1, 1))
+            # Rayleigh-Ritz in the block: Bm = Zr Yr^h (Hermitian PSD), rotate both to the Ritz basis
+            Bm = torch.empty((Bn, blk, blk), dtype=C128, device=G.device)
+            p.contract(Zr, (1, 1, 1), Yr.permute(0, 2, 1), (1, 1, 1), Bm, (1, 1, 1), conjB=True)
+            theta, Wh = p.eigh_psd(Bm, self.jacobi_tol)
+            Yn = torch.empty_like(Yr)
+            Zn = torch.empty_like(Zr)
+            p.contract(Wh, (1, 1, 1), Yr, (1, 1, 1), Yn, (1, 1, 1))
+            p.contract(Wh, (1, 1, 1), Zr, (1, 1, 1), Zn, (1, 1, 1))
+            Yr, Zr = Yn, Zn
+            # residual rows of the kept pairs: Zr[:k] - theta * Yr[:k]
+            Rr = Zr[:, :k, :].clone()
+            p.contract(p.rowscale(torch.eye(k, dtype=C128, device=G.device).expand(Bn, k, k).contiguous(), theta, k,
+                                  1.0, 0.0, 0, C128), (1, 1, 1), Yr[:, :k, :], (1, 1, 1), Rr, (1, 1, 1), alpha=-1.0, beta=1.0)
+            Rg = self._gram_rows(Rr, (1, 1, 1))
+            res = Rg.diagonal(dim1=1, dim2=2).real.clamp_min(0).sqrt()
+            worst = (res.max(dim=1).values / theta[:, 0].clamp_min(1e-300)).max().item()   # SYNC
+            self.stats['topk_iters'] = it + 1
+            if worst <= tol:
+                return theta[:, :k].contiguous(), Yr[:, :k, :].contiguous()
+        return None
+
     def kappa_truncate(self, T, kappa, max_err=None):
         """T [B,l,2,a,r] -> U.S over the inner index: [B,l,2,k,r], k = min(kappa, a) (and the relative rule)."""
         p = self.p
         Bn, l, _, a, r = T.shape
         Tv = T.permute(0, 1, 2, 4, 3)                           # [b | l,s,r | a]
         G = self._gram_cols(Tv, (1, 3, 1))                      # G = T^h T over (l,s,r)
+        if max_err is None and kappa is not None and a >= 64 and a >= 8 * kappa:
+            top = self.eigh_topk(G, kappa)
+            if top is not None:
+                theta, Vt = top
+                tr = G.diagonal(dim1=1, dim2=2).real.sum(dim=1)
+                disc = (tr - theta.sum(dim=1)).clamp_min(0).sqrt().unsqueeze(1)   # norm of what was discarded
+                T_n = self._empty((Bn, l, 2, kappa, r), T)
+                # T'[l,s,j,r] = sum_a V[a,j] T[l,s,a,r]
+                p.contract(Vt.to(self.dtype), (1, 1, 1), T.permute(0, 3, 1, 2, 4), (1, 1, 3),
+                           T_n.permute(0, 3, 1, 2, 4), (1, 1, 3))
+                return T_n, disc
         lam, Vh = p.eigh_psd(G, self.jacobi_tol)
         k = self._keep(lam, kappa, max_err, True, squared=True)
         disc = lam[:, k:].clamp_min(0).sqrt()

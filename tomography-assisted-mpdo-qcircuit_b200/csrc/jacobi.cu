@@ -320,6 +320,21 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
       int rc = check_launch("jacobi_kernel");
       if (rc) return rc;
     }
+    // SYNC (multi-launch mode only): read this sweep's rotation counters back and stop once every matrix of
+    // the batch has converged, instead of enqueueing no-op rounds up to maxSweeps.
+    static int* hCnt = nullptr;
+    static int hCap = 0;
+    if (hCap < batch) {
+      if (hCnt) cudaFreeHost(hCnt);
+      MPDO_CUDA(cudaMallocHost(&hCnt, sizeof(int) * (size_t)batch));
+      hCap = batch;
+    }
+    MPDO_CUDA(cudaMemcpy2DAsync(hCnt, sizeof(int), work + sw, sizeof(int) * WORK_INTS, sizeof(int), batch,
+                                cudaMemcpyDeviceToHost, st));
+    MPDO_CUDA(cudaStreamSynchronize(st));
+    bool any = false;
+    for (int i = 0; i < batch; ++i) any |= (hCnt[i] != 0);
+    if (!any) break;
   }
   return 0;
 }
