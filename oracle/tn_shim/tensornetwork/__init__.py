@@ -31,6 +31,15 @@ except ImportError:                    # pragma: no cover
     _dec = None
 
 __version__ = '0.4.6-shim'
+randomized_svd_calls = 0   # how often the reference's randomized branch (decompositions.py:112-115) was taken
+
+
+def _svd(tensor, pivot, max_singular_values, max_truncation_err, relative):
+    global randomized_svd_calls
+    if tensor.numel() >= 10000 and max_singular_values is not None:
+        randomized_svd_calls += 1
+    return _dec.svd(torch, tensor, pivot, max_singular_values, max_truncation_err, relative)
+
 _UNNAMED_EDGE = '__unnamed_edge__'
 _UNNAMED_NODE = '__unnamed_node__'
 _collection_stack = []
@@ -343,7 +352,7 @@ def _attach(new_node, edges, offset, old_node):
 def split_node(node, left_edges, right_edges, max_singular_values=None, max_truncation_err=None, relative=False,
                left_name=None, right_name=None, edge_name=None):
     lnames, rnames = _split_prepare(node, left_edges, right_edges)
-    u, s, vh, trun = _dec.svd(torch, node.tensor, len(left_edges), max_singular_values, max_truncation_err, relative)
+    u, s, vh, trun = _svd(node.tensor, len(left_edges), max_singular_values, max_truncation_err, relative)
     sq = torch.sqrt(s)
     u_s = u * sq
     vh_s = sq.reshape([-1] + [1] * (vh.dim() - 1)) * vh
@@ -374,7 +383,7 @@ def split_node_full_svd(node, left_edges, right_edges, max_singular_values=None,
                         relative=False, left_name=None, middle_name=None, right_name=None, left_edge_name=None,
                         right_edge_name=None):
     lnames, rnames = _split_prepare(node, left_edges, right_edges)
-    u, s, vh, trun = _dec.svd(torch, node.tensor, len(left_edges), max_singular_values, max_truncation_err, relative)
+    u, s, vh, trun = _svd(node.tensor, len(left_edges), max_singular_values, max_truncation_err, relative)
     ln = left_edge_name if left_edge_name else '__left_svd_edge__'
     rn = right_edge_name if right_edge_name else '__right_svd_edge__'
     left = Node(u, name=left_name, axis_names=lnames + [ln])

@@ -75,8 +75,12 @@ for cls in ('MeasureX', 'MeasureY', 'MeasureZ', 'Reset0', 'Reset1'):
 
 
 # ---- (b) circuits ----------------------------------------------------------------------------------
-def brick(c, n, depth, seed, entangler='cz', ghz=True, trunc_after_1q=True):
+def brick(c, n, depth, seed, entangler='cz', ghz=True, trunc_after_1q=True, pre_u3=False):
     g = torch.Generator().manual_seed(seed)
+    if pre_u3:   # noiseless random rotations first: breaks the GHZ symmetry (no exactly degenerate cuts)
+        for q in range(n):
+            th, ph, la = (torch.rand(3, generator=g) * 2 * math.pi).tolist()
+            c.u3(th, ph, la, [q], True)
     if ghz:
         c.h(0)
         for i in range(n - 1):
@@ -97,10 +101,12 @@ def brick(c, n, depth, seed, entangler='cz', ghz=True, trunc_after_1q=True):
 
 
 def run(tag, n, dt, prog, **kw):
+    tn.randomized_svd_calls = 0
     c = Ref.TensorCircuit(qn=n, dtype=dt, device='cpu', **kw)
     prog(c)
     state = Ref.Tools.create_ket0Series(n, dtype=dt, device='cpu')
     c.evolve(state)
+    out[f'{tag}/randomized_svd_calls'] = np.array(tn.randomized_svd_calls)
     out[f'{tag}/shapes'] = np.array([str((nd.axis_names, tuple(nd.tensor.shape))) for nd in state])
     dmn = c.cal_dmNodes()
     out[f'{tag}/trace'] = npy(ref_dm.trace_rho(dmn))
@@ -127,17 +133,24 @@ def debug_py(c):  # test/debug.py:35-41
 run('debug_py_c64', 5, C64, debug_py, ideal=False, noiseType='realNoise', chiFileDict=files5, chi=4, kappa=4, chip='best')
 run('debug_py_c128', 5, C128, debug_py, ideal=False, noiseType='realNoise', chiFileDict=files5, chi=4, kappa=4, chip='best')
 for dt, tag in ((C64, 'c64'), (C128, 'c128')):
-    run(f'ideal_noise_n4_{tag}', 4, dt, lambda c: brick(c, 4, 2, 21), ideal=False, noiseType='idealNoise', chi=8,
-        kappa=3, chip='medium')
-    run(f'ideal_noise_n5_{tag}', 5, dt, lambda c: brick(c, 5, 3, 2), ideal=False, noiseType='idealNoise', chi=16,
-        kappa=3, chip='medium')
-    run(f'unified_n4_{tag}', 4, dt, lambda c: brick(c, 4, 2, 22), ideal=False, noiseType='unified', chi=6, kappa=4,
+    # full-SVD branch everywhere (randomized_svd_calls == 0 is recorded and asserted by the tests)
+    run(f'ideal_noise_n4_{tag}', 4, dt, lambda c: brick(c, 4, 2, 21, ghz=False), ideal=False, noiseType='idealNoise',
+        chi=4, kappa=2, chip='medium')
+    run(f'ideal_noise_n3_{tag}', 3, dt, lambda c: brick(c, 3, 3, 31, pre_u3=True), ideal=False, noiseType='idealNoise',
+        chi=4, kappa=2, chip='medium')
+    run(f'unified_n4_{tag}', 4, dt, lambda c: brick(c, 4, 2, 22), ideal=False, noiseType='unified', chi=4, kappa=2,
         chip='medium')
     run(f'ideal_n5_{tag}', 5, dt, lambda c: brick(c, 5, 3, 23), ideal=True, chi=4)
     run(f'notrunc_n3_{tag}', 3, dt, lambda c: brick(c, 3, 1, 24), ideal=False, noiseType='idealNoise', chip='worst')
     files4 = {'CZ': {f'{i}{i + 1}': CZ_DEFAULT for i in range(3)}, 'CP': {}}
     run(f'realnoise_rzz_n4_{tag}', 4, dt, lambda c: brick(c, 4, 2, 5, entangler='rzz', ghz=False, trunc_after_1q=False),
-        ideal=False, noiseType='realNoise', chiFileDict=files4, chi=8, kappa=4, chip='best')
+        ideal=False, noiseType='realNoise', chiFileDict=files4, chi=2, kappa=1, chip='best')
+    files3 = {'CZ': {f'{i}{i + 1}': CZ_DEFAULT for i in range(2)}, 'CP': {}}
+    run(f'realnoise_cz_n3_{tag}', 3, dt, lambda c: brick(c, 3, 3, 41, ghz=False, trunc_after_1q=False), ideal=False,
+        noiseType='realNoise', chiFileDict=files3, chi=4, kappa=2, chip='best')
+    # the reference's randomized branch is taken here (numel >= 10000): loose pin only
+    run(f'ideal_noise_n5_{tag}', 5, dt, lambda c: brick(c, 5, 3, 2), ideal=False, noiseType='idealNoise', chi=16,
+        kappa=3, chip='medium')
 
 np.savez_compressed(os.path.join(HERE, 'reference_golden.npz'), **out)
 print('wrote', len(out), 'arrays to', os.path.join(HERE, 'reference_golden.npz'))

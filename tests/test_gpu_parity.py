@@ -85,3 +85,32 @@ def test_batched_circuits_match_single(cuda_prims):
         singles.append(E.dense_rho(Ts)[0].cpu())
     for oc, rho in zip(ocs, singles):
         assert rel(rho, oc.cal_dm()) < 1e-10
+
+
+# ---------------------------------------------------------------------------------------------------
+# the public API on the CUDA path against the golden vectors produced by the unmodified reference
+# ---------------------------------------------------------------------------------------------------
+import test_golden as tg  # noqa: E402
+
+
+@pytest.mark.parametrize('name', sorted(tg.CIRCUITS))
+@pytest.mark.parametrize('tag', ['c128', 'c64'])
+def test_cuda_api_matches_reference_golden(cuda_prims, name, tag):
+    import MPDOSimulator as Simulator
+    from MPDOSimulator import dmOperations
+    n, prog, kw = tg.CIRCUITS[name]
+    dt = tg.DT[tag]
+    c = Simulator.TensorCircuit(qn=n, dtype=dt, device='cuda:0', **kw)
+    prog(c)
+    st = Simulator.Tools.create_ket0Series(n, dtype=dt, device='cpu')      # host buffers in
+    c.evolve(st)
+    assert all(node.data.is_cuda for node in st)
+    tol = tg.tolerance(name, tag)
+    dmn = c.cal_dmNodes()
+    assert abs(dmOperations.trace_rho(dmn).item() - float(tg.GOLD[f'{name}_{tag}/trace'])) <= tol
+    if name in tg.TIES:
+        return
+    assert tg.close(c.cal_dm().cpu(), tg.t(f'{name}_{tag}/dm'), tol)
+    assert abs(dmOperations.trace_rho2(dmn).item() - float(tg.GOLD[f'{name}_{tag}/trace_rho2'])) <= tol
+    for q in range(n):
+        assert abs(dmOperations.pauli_expect(dmn, 2, q).item() - float(tg.GOLD[f'{name}_{tag}/pauli_z'][q])) <= tol

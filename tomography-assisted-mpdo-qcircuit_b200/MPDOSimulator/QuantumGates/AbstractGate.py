@@ -34,7 +34,7 @@ class Barrier(nn.Module):
 
 def assemble(rows, dtype, device='cpu'):
     """Stack a nested list of scalars / 0-d / 1-d tensors into [..., n, n] (batch axis first if any)."""
-    flat = [torch.as_tensor(x).to(dtype) if not isinstance(x, Tensor) else x.to(dtype) for r in rows for x in r]
+    flat = [torch.tensor(x, dtype=dtype) if not isinstance(x, Tensor) else x.to(dtype) for r in rows for x in r]
     batch = max([x.numel() for x in flat])
     flat = [x.reshape(-1).expand(batch) if x.numel() in (1, batch) else x for x in flat]
     n = len(rows)
