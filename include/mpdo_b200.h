@@ -92,6 +92,15 @@ int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t batchStrid
 int mpdo_rows_finalize(int batch, int n, int m, int mz, int ld, int64_t batchStride, const void* Y, double* s,
                        void* Yn, void* Z, int normalize, double zeroTol, void* stream);
 
+/* One call for the two small-core decompositions of the path: builds Y = [L | I] (L dense [b,n,m], Y scratch
+ * [b,n,m+n], both complex128), runs mpdo_jacobi_rows on it and mpdo_rows_finalize into s / Yn / Z.
+ *   SVD of L = Uh^h diag(s) Wh :  Yn = Wh (normalize = 1), Z = Uh
+ *   eigen-decomposition of a Hermitian PSD G (m = n): rows of J.G are lam_j v_j^h, so s = lam, Z = Vh, Yn = NULL.
+ * SYNC when the matrix needs more than one block pair (the sweep loop then polls convergence from the host).
+ * Replaces: torch.linalg.svd at decompositions.py:45,113 (and, through the Gram matrices, torch.linalg.qr :187). */
+int mpdo_decompose_rows(int batch, int n, int m, const void* L, void* Y, int32_t* work, double* s, void* Yn,
+                        void* Z, int normalize, double zeroTol, double tol, int maxSweeps, void* stream);
+
 /* X[b,j,c] = f(lam[b,j]) * V[b,j,c] for j < rows, c < cols, with f(x) = x^power and
  *   mode 0: f = 0 where lam[b,j] <= tol*lam[b,0]      (drop numerically null directions)
  *   mode 1: lam clamped from below at tol*lam[b,0]    (floor, for the first pass of a two-pass orthogonalisation)

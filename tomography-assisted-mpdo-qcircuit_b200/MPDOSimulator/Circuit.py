@@ -16,6 +16,7 @@ from torch.linalg import LinAlgError  # noqa: F401  (part of the reference's err
 
 from . import _engine
 from ._node import DenseNode, replicate_nodes
+from ._engine.strands import hand_over, run_strands
 from .AbstractCircuit import QuantumCircuit
 from .NoiseChannel import NoiseChannel
 from .QuantumGates.AbstractGate import QuantumGate
@@ -136,7 +137,6 @@ class TensorCircuit(QuantumCircuit):
         _qNodes[hi].has_left = True
         if noisy:
             _qNodes[hi].has_inner = True
-            self.last_stats['noisy_2q_updates'] = self.last_stats.get('noisy_2q_updates', 0) + 1
 
     def _apply_single_qubit_gate(self, _qNodes: List[DenseNode], _qubits, gate: QuantumGate,
                                  _oqs: Union[int, List[int]]):
@@ -184,9 +184,11 @@ class TensorCircuit(QuantumCircuit):
         self.last_stats = {'noisy_2q_updates': 0}
 
         layers = list(self.layers)   # nn.Sequential indexing is O(n) per access
+        segment = []                 # gates since the last truncate: independent qubit groups run concurrently
         for _i, layer in enumerate(layers):
             name = layer.name.lower()
             if 'truncate' in name:
+                self._run_segment(state, segment)
                 if checkConnectivity(state):
                     bondTruncate(state, max_singular_values=self.chi, max_truncation_err=self.max_truncation_err)
                     if not self.ideal:
@@ -195,11 +197,56 @@ class TensorCircuit(QuantumCircuit):
             elif 'barrier' in name:
                 pass
             else:
-                self._add_gate(state, _i, _oqs=self._oqs_list[_i], _gate=layer)
+                segment.append((_i, layer, self._oqs_list[_i]))
+        self._run_segment(state, segment)
 
         if not self.ideal and layers and 'truncate' not in layers[-1].name:
             svdKappa_left2right(state, max_singular_values=self.kappa, max_truncation_err=self.max_truncation_err)
         self._stateNodes = state
+
+    def _run_segment(self, state: List[DenseNode], segment: list):
+        """Apply the gates collected since the last truncate. Gates are grouped into strands of qubits that do
+        not interact inside the segment (order inside a strand is the circuit order); strands are independent,
+        so they are issued concurrently (one CUDA stream each, _engine/strands.py)."""
+        if not segment:
+            return
+        ops = [(i, g, oqs) for i, g, oqs in segment if oqs and oqs[0] is not None]
+        segment.clear()
+        for _, _, oqs in ops:
+            if not isinstance(oqs, List):
+                raise TypeError('Operating qubits must be a list.')
+            if max(oqs) >= self.qnumber:
+                raise ValueError(f'Qubit index out of range, max index is Q{max(oqs)}.')
+        parent = list(range(self.qnumber))
+
+        def find(x):
+            while parent[x] != x:
+                parent[x] = parent[parent[x]]
+                x = parent[x]
+            return x
+
+        for _, _, oqs in ops:
+            for q in oqs[1:]:
+                parent[find(q)] = find(oqs[0])
+        strands = {}
+        for op in ops:
+            strands.setdefault(find(op[2][0]), []).append(op)
+        for _, g, _ in ops:
+            if isinstance(g, QuantumGate) and not g.single and ((self.idealNoise and not g.ideal) or self.realNoise):
+                self.last_stats['noisy_2q_updates'] = self.last_stats.get('noisy_2q_updates', 0) + 1
+
+        def make(chain):
+            def task():
+                for i, g, oqs in chain:
+                    self._add_gate(state, i, _oqs=oqs, _gate=g)
+            return task
+
+        tasks = [make(chain) for chain in strands.values()]
+        parallel = getattr(_engine.get_prims(), 'name', '') == 'cuda'
+        run_strands(tasks, self.device, enabled=parallel)
+        if parallel and len(tasks) > 1:
+            for q in {q for _, _, oqs in ops for q in oqs}:
+                hand_over(state[q].data, self.device)
 
     def forward(self, state: List[DenseNode]):
         self.evolve(state)

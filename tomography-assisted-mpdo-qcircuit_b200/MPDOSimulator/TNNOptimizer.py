@@ -4,6 +4,7 @@ of CUDA launches (see _engine/steps.py); there is no CPU path."""
 from typing import List, Optional
 
 from . import _engine
+from ._engine.strands import hand_over, run_strands
 from ._node import DenseNode
 
 __all__ = ['qr_left2right', 'svd_left2right', 'svd_right2left', 'svdKappa_left2right', 'bondTruncate',
@@ -77,9 +78,23 @@ def svdKappa_left2right(_qubits: List[DenseNode], max_singular_values: Optional[
         return None
     _validate_qubit_list(_qubits, "svdKappa_left2right")
     eng = _engine_of(_qubits)
+    todo = []
     for q in _qubits:
         if max_singular_values is not None and (not q.has_inner or q.data.shape[3] <= max_singular_values):
             continue
         if not q.has_inner:
             raise ValueError(f'Axis name I_{q.index} not found')
-        q.data, _ = eng.kappa_truncate(q.data, max_singular_values, max_truncation_err)
+        todo.append(q)
+
+    def make(q):
+        def task():
+            q.data, _ = eng.kappa_truncate(q.data, max_singular_values, max_truncation_err)
+        return task
+
+    # sites are independent: issue them concurrently (one CUDA stream each)
+    device = _qubits[0].data.device
+    parallel = getattr(_engine.get_prims(), 'name', '') == 'cuda'
+    run_strands([make(q) for q in todo], device, enabled=parallel)
+    if parallel and len(todo) > 1:
+        for q in todo:
+            hand_over(q.data, device)

@@ -37,6 +37,8 @@ SYMBOLS = {
                                                   C.c_void_p]),
     'mpdo_rows_finalize': (C.c_int, [C.c_int] * 5 + [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                     C.c_int, C.c_double, C.c_void_p]),
+    'mpdo_decompose_rows': (C.c_int, [C.c_int] * 3 + [C.c_void_p] * 6 + [C.c_int, C.c_double, C.c_double, C.c_int,
+                                                                    C.c_void_p]),
     'mpdo_rowscale': (C.c_int, [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
                                                C.c_int, C.c_void_p, C.c_void_p]),
     'mpdo_rank_rule': (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,

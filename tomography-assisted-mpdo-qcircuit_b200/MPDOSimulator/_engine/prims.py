@@ -82,7 +82,8 @@ class CudaPrims:
     # -- plumbing ---------------------------------------------------------------------------------
     @staticmethod
     def _stream():
-        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        # raw handle of torch's current stream on the current device (thread-local, cheap)
+        return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
 
     @staticmethod
     def _ptr(t):
@@ -141,42 +142,30 @@ class CudaPrims:
         return out
 
     # -- small cores --------------------------------------------------------------------------------
-    def _jacobi(self, Y, n, m, mt, tol, sweeps):
-        Bn = Y.shape[0]
-        work = torch.empty((Bn, 48), dtype=torch.int32, device=Y.device)
+    def _decompose(self, L, want_rows, normalize, zero_tol, tol, sweeps):
+        Bn, n, m = L.shape
+        assert L.dtype == torch.complex128 and L.is_contiguous()
+        dev = L.device
+        Y = torch.empty((Bn, n, m + n), dtype=torch.complex128, device=dev)
+        work = torch.empty((Bn, 48), dtype=torch.int32, device=dev)
+        s = torch.empty((Bn, n), dtype=torch.float64, device=dev)
+        Z = torch.empty((Bn, n, n), dtype=torch.complex128, device=dev)
+        Yn = torch.empty((Bn, n, m), dtype=torch.complex128, device=dev) if want_rows else None
         tol = max(tol, 4.4e-16 * (m ** 0.5))   # rounding level of a length-m dot product
-        _lib.check(self.lib.mpdo_jacobi_rows(Bn, n, m, mt, Y.shape[2], Y.stride(0), self._ptr(Y), tol, sweeps,
-                                             self._ptr(work), self._stream()), 'mpdo_jacobi_rows')
-        return work
+        _lib.check(self.lib.mpdo_decompose_rows(Bn, n, m, self._ptr(L), self._ptr(Y), self._ptr(work), self._ptr(s),
+                                                self._ptr(Yn) if want_rows else None, self._ptr(Z), int(normalize),
+                                                float(zero_tol), float(tol), int(sweeps), self._stream()),
+                   'mpdo_decompose_rows')
+        return s, Yn, Z
 
     def eigh_psd(self, G, tol=1e-15, sweeps=30):
         """Hermitian PSD G [B,n,n] (complex128) -> lam [B,n] descending, Vh [B,n,n] with G = Vh^h diag(lam) Vh."""
-        Bn, n, _ = G.shape
-        assert G.dtype == torch.complex128
-        Y = torch.zeros((Bn, n, 2 * n), dtype=torch.complex128, device=G.device)
-        Y[:, :, :n].copy_(G)
-        Y[:, :, n:].diagonal(dim1=1, dim2=2).fill_(1.0)
-        self._jacobi(Y, n, n, 2 * n, tol, sweeps)
-        lam = torch.empty((Bn, n), dtype=torch.float64, device=G.device)
-        Vh = torch.empty((Bn, n, n), dtype=torch.complex128, device=G.device)
-        _lib.check(self.lib.mpdo_rows_finalize(Bn, n, n, n, 2 * n, Y.stride(0), self._ptr(Y), self._ptr(lam), None,
-                                               self._ptr(Vh), 0, 0.0, self._stream()), 'mpdo_rows_finalize')
+        lam, _, Vh = self._decompose(G.contiguous(), False, 0, 0.0, tol, sweeps)
         return lam, Vh
 
     def svd_rows(self, L, tol=1e-15, sweeps=30, zero_tol=1e-300):
         """L [B,n,m] (complex128) = Uh^h diag(s) Wh -> (Uh [B,n,n], s [B,n] descending, Wh [B,n,m])."""
-        Bn, n, m = L.shape
-        assert L.dtype == torch.complex128
-        Y = torch.zeros((Bn, n, m + n), dtype=torch.complex128, device=L.device)
-        Y[:, :, :m].copy_(L)
-        Y[:, :, m:].diagonal(dim1=1, dim2=2).fill_(1.0)
-        self._jacobi(Y, n, m, m + n, tol, sweeps)
-        s = torch.empty((Bn, n), dtype=torch.float64, device=L.device)
-        Wh = torch.empty((Bn, n, m), dtype=torch.complex128, device=L.device)
-        Uh = torch.empty((Bn, n, n), dtype=torch.complex128, device=L.device)
-        _lib.check(self.lib.mpdo_rows_finalize(Bn, n, m, n, m + n, Y.stride(0), self._ptr(Y), self._ptr(s),
-                                               self._ptr(Wh), self._ptr(Uh), 1, zero_tol, self._stream()),
-                   'mpdo_rows_finalize')
+        s, Wh, Uh = self._decompose(L.contiguous(), True, 1, zero_tol, tol, sweeps)
         return Uh, s, Wh
 
     def rowscale(self, V, lam, rows, power, tol, mode, dtype):

@@ -1,0 +1,74 @@
+"""Concurrent execution of independent pieces of one layer ("strands").
+
+Between two truncate() markers the gates of a brickwork layer fall into groups of qubits that never
+interact (a brick pair with its single-qubit rotations, or a lone qubit); likewise the inner-index
+truncation treats every site on its own. Each strand is a short chain of small kernels (single-CTA Jacobi
+decompositions, skinny contractions) that cannot fill 148 SMs alone, so strands are issued from a few host
+threads, each on its own CUDA stream: the kernels of different brick pairs overlap on the device and the
+host-side waits (rank read-backs) overlap too. The main stream waits for every side stream afterwards, so
+callers see ordinary stream-ordered semantics.
+"""
+import threading
+from concurrent.futures import ThreadPoolExecutor
+
+import torch
+
+_POOL = None
+_STREAMS = {}
+_LOCK = threading.Lock()
+MAX_WORKERS = 12
+
+
+def _pool():
+    global _POOL
+    if _POOL is None:
+        _POOL = ThreadPoolExecutor(max_workers=MAX_WORKERS, thread_name_prefix='mpdo-strand')
+    return _POOL
+
+
+def _streams(device, count):
+    key = str(device)
+    with _LOCK:
+        have = _STREAMS.setdefault(key, [])
+        while len(have) < count:
+            have.append(torch.cuda.Stream(device=device))
+        return have[:count]
+
+
+def run_strands(tasks, device, enabled=True):
+    """tasks: list of zero-argument callables, mutually independent. Runs them concurrently on side streams when
+    it pays off (CUDA device, more than one task), else in order on the current stream."""
+    dev = torch.device(device)
+    if not enabled or len(tasks) < 2 or dev.type != 'cuda':
+        for t in tasks:
+            t()
+        return
+    main = torch.cuda.current_stream(dev)
+    nworkers = min(len(tasks), MAX_WORKERS)
+    streams = _streams(dev, nworkers)
+    for s in streams:
+        s.wait_stream(main)
+    errors = []
+
+    def work(wid):
+        try:
+            with torch.cuda.device(dev), torch.cuda.stream(streams[wid]):
+                for t in tasks[wid::nworkers]:
+                    t()
+        except BaseException as exc:  # re-raised in the caller's thread
+            errors.append(exc)
+
+    futures = [_pool().submit(work, w) for w in range(nworkers)]
+    for f in futures:
+        f.result()
+    for s in streams:
+        main.wait_stream(s)
+    if errors:
+        raise errors[0]
+
+
+def hand_over(tensor, device):
+    """A tensor produced on a side stream is about to live on (and later be freed from) the main stream."""
+    if tensor.is_cuda:
+        tensor.record_stream(torch.cuda.current_stream(torch.device(device)))
+    return tensor

@@ -4,12 +4,14 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/mpdo_b200.h"
 
 namespace mpdo {
 
 extern thread_local char g_err[512];
-extern long long g_launches;
+extern std::atomic<long long> g_launches;
 
 inline int fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);

@@ -5,7 +5,7 @@
 namespace mpdo {
 
 thread_local char g_err[512] = "";
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 // Tout[bl, p, g, e] = sum_s G[p, s, g] * T[bl, s, e]     (e = (a, r) flattened, bl = (batch, l))
 // One thread per (bl, e): two coalesced loads, 2K coalesced stores. Algorithmic traffic:
@@ -197,7 +197,7 @@ extern "C" int mpdo_cast(int dtypeIn, int dtypeOut, int64_t count, const void* i
 
 extern "C" int mpdo_version(void) { return 100; }
 extern "C" const char* mpdo_last_error(void) { return mpdo::g_err; }
-extern "C" int64_t mpdo_launch_count(void) { return mpdo::g_launches; }
+extern "C" int64_t mpdo_launch_count(void) { return mpdo::g_launches.load(); }
 extern "C" int mpdo_device_info(int* smCount, int* smemPerBlockOptin, int* ccMajor, int* ccMinor) {
   using namespace mpdo;
   int dev = 0;

@@ -256,6 +256,27 @@ __global__ void __launch_bounds__(256) rows_finalize_kernel(int n, int m, int mz
   }
 }
 
+// Y[b, i, 0..m) = L[b, i, 0..m),  Y[b, i, m + j] = (i == j): the matrix followed by the identity that will
+// accumulate the row mixing.
+__global__ void __launch_bounds__(256) rows_setup_kernel(int n, int m, const double2* __restrict__ L,
+                                                         double2* __restrict__ Y) {
+  const long long b = blockIdx.y;
+  const int mt = m + n;
+  const long long total = (long long)n * mt;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / mt), c = (int)(idx % mt);
+    double2 v;
+    if (c < m) {
+      v = L[(b * n + i) * m + c];
+    } else {
+      v.x = (c - m == i) ? 1.0 : 0.0;
+      v.y = 0.0;
+    }
+    Y[b * total + idx] = v;
+  }
+}
+
 }  // namespace mpdo
 
 extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t batchStride, void* Y, double tol,
@@ -322,8 +343,8 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
     }
     // SYNC (multi-launch mode only): read this sweep's rotation counters back and stop once every matrix of
     // the batch has converged, instead of enqueueing no-op rounds up to maxSweeps.
-    static int* hCnt = nullptr;
-    static int hCap = 0;
+    static thread_local int* hCnt = nullptr;
+    static thread_local int hCap = 0;
     if (hCap < batch) {
       if (hCnt) cudaFreeHost(hCnt);
       MPDO_CUDA(cudaMallocHost(&hCnt, sizeof(int) * (size_t)batch));
@@ -349,4 +370,22 @@ extern "C" int mpdo_rows_finalize(int batch, int n, int m, int mz, int ld, int64
   rows_finalize_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(n, m, mz, ld, batchStride, (const double2*)Y, s,
                                                                   (double2*)Yn, (double2*)Z, normalize, zeroTol);
   return check_launch("rows_finalize_kernel");
+}
+
+extern "C" int mpdo_decompose_rows(int batch, int n, int m, const void* L, void* Y, int32_t* work, double* s,
+                                   void* Yn, void* Z, int normalize, double zeroTol, double tol, int maxSweeps,
+                                   void* stream) {
+  using namespace mpdo;
+  if (batch <= 0 || n <= 0) return 0;
+  if (!L || !Y || !work || !s || m <= 0) return fail(MPDO_EINVAL, "mpdo_decompose_rows: bad argument");
+  if (batch > 65535) return fail(MPDO_EINVAL, "mpdo_decompose_rows: batch > 65535");
+  const int mt = m + n;
+  const long long total = (long long)n * mt;
+  unsigned gx = (unsigned)((total + 255) / 256 > 2048 ? 2048 : (total + 255) / 256);
+  rows_setup_kernel<<<dim3(gx, batch), 256, 0, (cudaStream_t)stream>>>(n, m, (const double2*)L, (double2*)Y);
+  int rc = check_launch("rows_setup_kernel");
+  if (rc) return rc;
+  rc = mpdo_jacobi_rows(batch, n, m, mt, mt, total, Y, tol, maxSweeps, work, stream);
+  if (rc) return rc;
+  return mpdo_rows_finalize(batch, n, m, n, mt, total, Y, s, Yn, Z, normalize, zeroTol, stream);
 }
