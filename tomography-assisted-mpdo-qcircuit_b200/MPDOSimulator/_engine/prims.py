@@ -78,6 +78,7 @@ class CudaPrims:
         _lib.check(self.lib.mpdo_device_info(C.byref(sm), C.byref(smem), C.byref(major), C.byref(minor)),
                    'mpdo_device_info')
         self.sm_count = sm.value
+        self._desc_cache = {}
 
     # -- plumbing ---------------------------------------------------------------------------------
     @staticmethod
@@ -95,6 +96,26 @@ class CudaPrims:
     # -- contraction --------------------------------------------------------------------------------
     def contract(self, A, ra, B, rb, Cv, rc, conjA=False, conjB=False, acc64=None, alpha=1.0, beta=0.0):
         """Cv[b,i,j] = alpha * sum_k op(A[b,i,k]) op(B[b,k,j]) + beta * Cv[b,i,j] on strided views."""
+        # descriptors depend only on the geometry of the three views: cache them (the same few dozen geometries
+        # recur in every layer, and building one costs more host time than launching the kernel)
+        key = (A.shape, A.stride(), A.dtype, ra, B.shape, B.stride(), B.dtype, rb, Cv.shape, Cv.stride(), Cv.dtype, rc,
+               conjA, conjB, acc64, alpha, beta)
+        hit = self._desc_cache.get(key)
+        if hit is None:
+            hit = self._build_desc(A, ra, B, rb, Cv, rc, conjA, conjB, acc64, alpha, beta)
+            if len(self._desc_cache) < 4096:
+                self._desc_cache[key] = hit
+        d, ksplit = hit
+        if ksplit > 1:
+            if beta == 0.0:
+                Cv.zero_()
+            elif beta != 1.0:
+                Cv.mul_(beta)
+        _lib.check(self.lib.mpdo_contract(C.byref(d), self._ptr(A), self._ptr(B), self._ptr(Cv), self._stream()),
+                   'mpdo_contract')
+        return Cv
+
+    def _build_desc(self, A, ra, B, rb, Cv, rc, conjA, conjB, acc64, alpha, beta):
         (ab, ai, ak), (bb, bk, bj), (cb, ci, cj) = split_roles(A, ra), split_roles(B, rb), split_roles(Cv, rc)
         M, K, N = _prod(ai[0]), _prod(ak[0]), _prod(bj[0])
         batch = _prod(ab[0])
@@ -120,14 +141,7 @@ class CudaPrims:
             ksplit = max(1, min((K + 255) // 256, (4 * self.sm_count) // max(tiles, 1)))
         d.ksplit = ksplit
         d.alpha, d.beta = float(alpha), float(beta)
-        if ksplit > 1:
-            if beta == 0.0:
-                Cv.zero_()
-            elif beta != 1.0:
-                Cv.mul_(beta)
-        _lib.check(self.lib.mpdo_contract(C.byref(d), self._ptr(A), self._ptr(B), self._ptr(Cv), self._stream()),
-                   'mpdo_contract')
-        return Cv
+        return d, ksplit
 
     # -- single-qubit absorption --------------------------------------------------------------------
     def absorb_1q(self, T, G):
