@@ -1,0 +1,200 @@
+#!/usr/bin/env python
+"""Runs the five BASELINE.json configurations (SURVEY 8d definitions) through the public API on one GPU and
+prints one JSON line per configuration: throughput (noisy 2q updates/s, circuits/s for the batched config) and
+size-independent sanity properties (Tr rho, Hermiticity / positivity of reduced density matrices, agreement of a
+batched run with single runs). Not the driver's bench (that is bench.py, cfg2); this is the coverage run whose
+output is kept under profiles/.
+
+    python bench_configs.py --configs 1,2,3,4,5 [--depth-scale 0.25] [--out profiles/r1_configs.jsonl]
+"""
+import argparse
+import json
+import math
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, 'tomography-assisted-mpdo-qcircuit_b200')
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+import MPDOSimulator as Simulator  # noqa: E402
+from MPDOSimulator import dmOperations  # noqa: E402
+
+C64, C128 = torch.complex64, torch.complex128
+
+
+def chi_file():
+    return os.path.join(PKG, 'MPDOSimulator', 'chi', 'czDefault.mat')
+
+
+def angles(seed_ids, n_draws):
+    """U[0, 2 pi) angles from torch.Generator().manual_seed(1234 + circuit_id); [n_draws, B] (B = 1 -> floats)."""
+    cols = []
+    for cid in seed_ids:
+        g = torch.Generator().manual_seed(1234 + cid)
+        cols.append(torch.rand(n_draws, generator=g, dtype=torch.float64) * 2 * math.pi)
+    return torch.stack(cols, dim=1)
+
+
+def brickwork(c, n, depth, ang, entangler, prefix_ghz=False, trunc_after_1q=True):
+    """layer d = [u3 on every qubit ; truncate ; entangler on bonds q = d mod 2 ; truncate]."""
+    updates = 0
+    B = ang.shape[1]
+    pick = (lambda t: float(t[0])) if B == 1 else (lambda t: t.clone())
+    k = 0
+    if prefix_ghz:
+        c.h(0)
+        for i in range(n - 1):
+            c.cnot(i, i + 1)
+            updates += 1
+        c.truncate()
+    for d in range(depth):
+        for q in range(n):
+            c.u3(pick(ang[k]), pick(ang[k + 1]), pick(ang[k + 2]), [q])
+            k += 3
+        if trunc_after_1q:
+            c.truncate()
+        for q in range(d % 2, n - 1, 2):
+            if entangler == 'rzz':
+                c.rzz(pick(ang[k]), q, q + 1)
+                k += 1
+                updates += 2
+            else:
+                getattr(c, entangler)(q, q + 1)
+                updates += 1
+        c.truncate()
+    return updates
+
+
+def n_draws(n, depth, entangler):
+    per_layer = 3 * n + (n // 2 + 1 if entangler == 'rzz' else 0)
+    return per_layer * depth + 8
+
+
+def rdm_checks(circ, n):
+    """Hermiticity and smallest eigenvalue of the two-site reduced density matrix in the middle of the chain."""
+    eng = circ._engine()
+    Ts = circ._Ts()
+    mid = n // 2
+    rho = eng.dense_rho(Ts, keep=[mid, mid + 1])[0].cpu()
+    herm = (rho - rho.mH).abs().max().item() / rho.abs().max().item()
+    ev = torch.linalg.eigvalsh((rho + rho.mH) / 2)
+    return {'rdm_hermiticity': herm, 'rdm_min_eig_over_trace': (ev.min() / ev.sum()).item()}
+
+
+def run_single(tag, n, depth, dtype, chi, kappa, noise, chip, entangler, prefix_ghz=False, trunc_after_1q=True,
+               files=None, readout=None):
+    dev = 'cuda:0'
+    ang = angles([0], n_draws(n, depth, entangler))
+    c = Simulator.TensorCircuit(qn=n, ideal=False, noiseType=noise, chiFileDict=files, chi=chi, kappa=kappa,
+                                chip=chip, dtype=dtype, device=dev)
+    updates = brickwork(c, n, depth, ang, entangler, prefix_ghz, trunc_after_1q)
+    state = Simulator.Tools.create_ket0Series(n, dtype=dtype, device='cpu')
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    c.evolve(state)
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    dmn = c.cal_dmNodes()
+    out = {'config': tag, 'qubits': n, 'depth': depth, 'chi': chi, 'kappa': kappa, 'dtype': str(dtype).split('.')[-1],
+           'noisy_2q_updates': updates, 'seconds': secs, 'updates_per_s': updates / secs,
+           'trace_rho': dmOperations.trace_rho(dmn).item(),
+           'max_bond': max(int(s.data.shape[4]) for s in state), 'max_inner': max(int(s.data.shape[3]) for s in state),
+           'peak_mem_GB': torch.cuda.max_memory_allocated() / 2 ** 30}
+    out.update(rdm_checks(c, n))
+    if readout == 'bitstrings':
+        g = torch.Generator().manual_seed(99)
+        bits = torch.randint(0, 2, (1024, n), generator=g).tolist()
+        t1 = time.perf_counter()
+        p = c.bitstring_probabilities(bits)
+        torch.cuda.synchronize()
+        out['bitstring_readout_seconds'] = time.perf_counter() - t1
+        out['bitstring_prob_min'] = p.min().item()
+        out['bitstring_prob_sum_of_1024'] = p.sum().item()
+    return out
+
+
+def run_batched(tag, n, depth, chi, kappa, total, chunk):
+    dev = 'cuda:0'
+    rows = []
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    Z = 2
+    for start in range(0, total, chunk):
+        ids = list(range(start, min(total, start + chunk)))
+        ang = angles(ids, n_draws(n, depth, 'cz'))
+        c = Simulator.TensorCircuit(qn=n, ideal=False, noiseType='idealNoise', chi=chi, kappa=kappa, chip='medium',
+                                    dtype=C64, device=dev)
+        brickwork(c, n, depth, ang, 'cz')
+        st = Simulator.Tools.create_ket0Series(n, dtype=C64, device='cpu')
+        c.evolve(st)
+        dmn = c.cal_dmNodes()
+        cols = [dmOperations.pauli_expect(dmn, Z, q) for q in range(n)]
+        cols += [dmOperations.pauli_expect(dmn, [Z, Z], [q, q + 1]) for q in range(n - 1)]
+        cols.append(c.bitstring_probabilities(['0' * n]).expand(len(ids)) if len(ids) == 1 else
+                    c._engine().chain_value_proj(c._Ts(), [0] * n))
+        rows.append(torch.stack([x.reshape(-1).to(torch.float64) for x in cols], dim=1))
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    table = torch.cat(rows).cpu()
+    # property: circuit 0 of the batch equals a single (unbatched) run of the same circuit
+    ang0 = angles([0], n_draws(n, depth, 'cz'))
+    c1 = Simulator.TensorCircuit(qn=n, ideal=False, noiseType='idealNoise', chi=chi, kappa=kappa, chip='medium',
+                                 dtype=C64, device=dev)
+    brickwork(c1, n, depth, ang0, 'cz')
+    s1 = Simulator.Tools.create_ket0Series(n, dtype=C64, device='cpu')
+    c1.evolve(s1)
+    d1 = c1.cal_dmNodes()
+    single = torch.stack([dmOperations.pauli_expect(d1, Z, q).reshape(()) for q in range(n)]).cpu().to(torch.float64)
+    return {'config': tag, 'qubits': n, 'depth': depth, 'chi': chi, 'kappa': kappa, 'dtype': 'complex64',
+            'circuits': total, 'chunk': chunk, 'seconds': secs, 'circuits_per_s': total / secs,
+            'readout_table_shape': list(table.shape),
+            'batch_vs_single_max_abs_diff_Z': (table[0, :n] - single).abs().max().item(),
+            'readout_finite': bool(torch.isfinite(table).all()),
+            'peak_mem_GB': torch.cuda.max_memory_allocated() / 2 ** 30}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--configs', default='1,2,3,4,5')
+    ap.add_argument('--depth-scale', type=float, default=1.0)
+    ap.add_argument('--qubit-scale', type=float, default=1.0)
+    ap.add_argument('--circuits', type=int, default=1024)
+    ap.add_argument('--chunk', type=int, default=128)
+    ap.add_argument('--out', default=None)
+    args = ap.parse_args()
+    ds = lambda d: max(1, int(round(d * args.depth_scale)))
+    qs = lambda q: max(4, int(round(q * args.qubit_scale)))
+    lines = []
+    for cfg in [int(x) for x in args.configs.split(',')]:
+        torch.cuda.reset_peak_memory_stats()
+        if cfg == 1:
+            r = run_single('cfg1', 10, ds(10), C64, 32, 4, 'idealNoise', 'medium', 'cz', prefix_ghz=True)
+        elif cfg == 2:
+            n = qs(20)
+            files = {'CZ': {f'{i}{i + 1}': chi_file() for i in range(n - 1)}, 'CP': {}}
+            r = run_single('cfg2', n, ds(20), C64, 64, 4, 'realNoise', 'best', 'rzz', trunc_after_1q=False, files=files)
+        elif cfg == 3:
+            r = run_single('cfg3', qs(50), ds(30), C128, 128, 8, 'idealNoise', 'medium', 'cz')
+        elif cfg == 4:
+            r = run_batched('cfg4', 16, ds(16), 64, 4, args.circuits, args.chunk)
+        elif cfg == 5:
+            r = run_single('cfg5', qs(100), ds(40), C64, 256, 8, 'idealNoise', 'medium', 'cz', readout='bitstrings')
+        else:
+            continue
+        r['depth_scale'], r['qubit_scale'] = args.depth_scale, args.qubit_scale
+        print(json.dumps(r), flush=True)
+        lines.append(r)
+    if args.out:
+        with open(args.out, 'a') as f:
+            for r in lines:
+                f.write(json.dumps(r) + '\n')
+
+
+if __name__ == '__main__':
+    main()

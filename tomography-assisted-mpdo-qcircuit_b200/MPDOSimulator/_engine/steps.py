@@ -464,6 +464,14 @@ class Engine:
             E = En
         return E.reshape(Bn)
 
+    def chain_value_proj(self, Ts, bits):
+        """<b|rho_c|b> of ONE bitstring b (list of 0/1) for every circuit c of the batch -> [B] float64."""
+        Bn = Ts[0].shape[0]
+        L = torch.ones((Bn, 1, 1), dtype=C128, device=Ts[0].device)
+        for k, T in enumerate(Ts):
+            L = self.transfer_proj(L, T, int(bits[k]))
+        return L.reshape(Bn).real
+
     def bitstring_probs(self, Ts, bits):
         """<b|rho|b> for bitstrings bits [NB, n] (0/1 ints) of one circuit (B = 1) -> [NB] float64."""
         bits = torch.as_tensor(bits).reshape(-1, len(Ts))
