@@ -16,7 +16,7 @@ from torch.linalg import LinAlgError  # noqa: F401  (part of the reference's err
 
 from . import _engine
 from ._node import DenseNode, replicate_nodes
-from ._engine.strands import hand_over, run_strands
+from ._engine.strands import adopt, hand_over, run_strands
 from .AbstractCircuit import QuantumCircuit
 from .NoiseChannel import NoiseChannel
 from .QuantumGates.AbstractGate import QuantumGate
@@ -237,12 +237,15 @@ class TensorCircuit(QuantumCircuit):
 
         def make(chain):
             def task():
+                if parallel:
+                    for q in {q for _, _, oqs in chain for q in oqs}:
+                        adopt(state[q].data)
                 for i, g, oqs in chain:
                     self._add_gate(state, i, _oqs=oqs, _gate=g)
             return task
 
+        parallel = getattr(_engine.get_prims(), 'name', '') == 'cuda' and len(strands) > 1
         tasks = [make(chain) for chain in strands.values()]
-        parallel = getattr(_engine.get_prims(), 'name', '') == 'cuda'
         run_strands(tasks, self.device, enabled=parallel)
         if parallel and len(tasks) > 1:
             for q in {q for _, _, oqs in ops for q in oqs}:

@@ -4,7 +4,7 @@ of CUDA launches (see _engine/steps.py); there is no CPU path."""
 from typing import List, Optional
 
 from . import _engine
-from ._engine.strands import hand_over, run_strands
+from ._engine.strands import adopt, hand_over, run_strands
 from ._node import DenseNode
 
 __all__ = ['qr_left2right', 'svd_left2right', 'svd_right2left', 'svdKappa_left2right', 'bondTruncate',
@@ -88,12 +88,14 @@ def svdKappa_left2right(_qubits: List[DenseNode], max_singular_values: Optional[
 
     def make(q):
         def task():
+            if parallel:
+                adopt(q.data)
             q.data, _ = eng.kappa_truncate(q.data, max_singular_values, max_truncation_err)
         return task
 
     # sites are independent: issue them concurrently (one CUDA stream each)
     device = _qubits[0].data.device
-    parallel = getattr(_engine.get_prims(), 'name', '') == 'cuda'
+    parallel = getattr(_engine.get_prims(), 'name', '') == 'cuda' and len(todo) > 1
     run_strands([make(q) for q in todo], device, enabled=parallel)
     if parallel and len(todo) > 1:
         for q in todo:

@@ -304,7 +304,9 @@ class Engine:
         Bn, n, _ = G.shape
         blk = min(n, max(2 * k, k + 28))
         tol = 1e-10 if self.f32 else 1e-12
-        key = (n, blk, str(G.device))
+        # one copy per CUDA stream: strands run this concurrently on different streams
+        stream_id = torch.cuda.current_stream(G.device).cuda_stream if G.is_cuda else 0
+        key = (n, blk, str(G.device), stream_id)
         if key not in self._omega:
             g = torch.Generator().manual_seed(20261017)
             om = torch.complex(torch.randn(blk, n, generator=g, dtype=torch.float64),

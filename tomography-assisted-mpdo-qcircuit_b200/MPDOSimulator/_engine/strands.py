@@ -67,6 +67,14 @@ def run_strands(tasks, device, enabled=True):
         raise errors[0]
 
 
+def adopt(tensor):
+    """Called inside a strand for every tensor that was produced on another stream: tells the caching allocator
+    that the current (side) stream uses it, so that its memory is not recycled under a kernel still reading it."""
+    if tensor.is_cuda:
+        tensor.record_stream(torch.cuda.current_stream(tensor.device))
+    return tensor
+
+
 def hand_over(tensor, device):
     """A tensor produced on a side stream is about to live on (and later be freed from) the main stream."""
     if tensor.is_cuda:
