@@ -1,0 +1,95 @@
+"""-m gpu: BASELINE configurations against oracle fixtures (tests/golden/config_fixtures.npz, written by
+tests/golden/make_cfg_fixtures.py with the oracle in exact complex128 / complex64 and in reference mode).
+
+cfg1 is run at full size (10 qubits, GHZ prefix, depth 10, chi 32, kappa 4); cfg2 as a 6-qubit depth-3 slice with
+the same chi-matrix channel, chi 64, kappa 4 (the full 20-qubit circuit takes the oracle tens of minutes).
+Quantities are gauge invariant: Tr rho, <Z_q>, <Z_q Z_q+1>, P(0...0), the two-site RDM in the middle.
+complex128 is held to the exact oracle; complex64 to max(1e-5, 3 x the oracle's own complex64-vs-complex128 gap)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import bench_configs as bc
+import MPDOSimulator as Simulator
+from MPDOSimulator import dmOperations
+
+pytestmark = pytest.mark.gpu
+FX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'config_fixtures.npz'))
+C64, C128 = torch.complex64, torch.complex128
+
+
+def gpu_quantities(circ, n):
+    dmn = circ.cal_dmNodes()
+    eng, Ts = circ._engine(), circ._Ts()
+    return {
+        'trace': np.array(dmOperations.trace_rho(dmn).item()),
+        'z': np.array([dmOperations.pauli_expect(dmn, 2, q).item() for q in range(n)]),
+        'zz': np.array([dmOperations.pauli_expect(dmn, [2, 2], [q, q + 1]).item() for q in range(n - 1)]),
+        'p0': np.array(circ.bitstring_probabilities(['0' * n])[0].item()),
+        'rdm_mid': eng.dense_rho(Ts, keep=[n // 2, n // 2 + 1])[0].cpu().numpy(),
+    }
+
+
+def compare(name, got, dt):
+    worst = 0.0
+    for key, val in got.items():
+        exact = FX[f'{name}/c128/exact/{key}']
+        scale = np.abs(exact).max()
+        err = np.abs(val - exact).max() / scale
+        if dt == 'c128':
+            tol = 1e-8
+        else:
+            floor = np.abs(FX[f'{name}/c64/exact/{key}'] - exact).max() / scale
+            tol = max(1e-5, 3 * floor)
+        print(f'{name} {dt} {key}: rel err {err:.2e} (tol {tol:.1e})')
+        assert err <= tol, (name, dt, key, err, tol)
+        worst = max(worst, err)
+    return worst
+
+
+@pytest.mark.parametrize('dt', ['c128', 'c64'])
+def test_cfg1_full_size(cuda_prims, dt):
+    n, depth = 10, 10
+    dtype = C128 if dt == 'c128' else C64
+    c = Simulator.TensorCircuit(qn=n, ideal=False, noiseType='idealNoise', chi=32, kappa=4, chip='medium',
+                                dtype=dtype, device='cuda:0')
+    bc.brickwork(c, n, depth, bc.angles([0], bc.n_draws(n, depth, 'cz')), 'cz', prefix_ghz=True)
+    st = Simulator.Tools.create_ket0Series(n, dtype=dtype, device='cpu')
+    c.evolve(st)
+    compare('cfg1', gpu_quantities(c, n), dt)
+
+
+@pytest.mark.parametrize('dt', ['c128', 'c64'])
+def test_cfg2_slice(cuda_prims, dt):
+    n, depth = 6, 3
+    dtype = C128 if dt == 'c128' else C64
+    files = {'CZ': {f'{i}{i + 1}': bc.chi_file() for i in range(n - 1)}, 'CP': {}}
+    c = Simulator.TensorCircuit(qn=n, ideal=False, noiseType='realNoise', chiFileDict=files, chi=64, kappa=4,
+                                chip='best', dtype=dtype, device='cuda:0')
+    bc.brickwork(c, n, depth, bc.angles([0], bc.n_draws(n, depth, 'rzz')), 'rzz', trunc_after_1q=False)
+    st = Simulator.Tools.create_ket0Series(n, dtype=dtype, device='cpu')
+    c.evolve(st)
+    compare('cfg2_n6_d3', gpu_quantities(c, n), dt)
+
+
+def test_batched_sweep_is_deterministic_and_matches_singles(cuda_prims):
+    """cfg4 in small: 6 circuits x 8 qubits as one batch, twice (strand concurrency must not change results), and
+    against the same circuits run one by one."""
+    n, depth, ids = 8, 4, list(range(6))
+
+    def run(id_list):
+        c = Simulator.TensorCircuit(qn=n, ideal=False, noiseType='idealNoise', chi=16, kappa=4, chip='medium',
+                                    dtype=C128, device='cuda:0')
+        bc.brickwork(c, n, depth, bc.angles(id_list, bc.n_draws(n, depth, 'cz')), 'cz')
+        st = Simulator.Tools.create_ket0Series(n, dtype=C128, device='cpu')
+        c.evolve(st)
+        dmn = c.cal_dmNodes()
+        return torch.stack([dmOperations.pauli_expect(dmn, 2, q).reshape(-1) for q in range(n)], 1).cpu()
+
+    a, b = run(ids), run(ids)
+    assert torch.equal(a, b) or (a - b).abs().max().item() < 1e-13
+    for i in ids:
+        single = run([i])
+        assert (a[i] - single[0]).abs().max().item() < 1e-10
