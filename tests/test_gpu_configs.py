@@ -32,33 +32,53 @@ def gpu_quantities(circ, n):
     }
 
 
-def compare(name, got, dt):
+def compare(name, got, dt, tie_floor=False):
+    """complex128: 1e-7 (the reference's absolute rank rule e*1e-8 discards up to 5e-8 of weight per split, and a
+    singular value within rounding of that threshold flips the kept rank; without that rule 1e-10 holds, see
+    test_gpu_parity). complex64: max(1e-5, 3 x the oracle's own complex64-vs-complex128 gap).
+    tie_floor: the circuit has exactly degenerate singular values at its cuts (GHZ symmetry x equally weighted
+    depolarizing branches), the reference's own answers spread (precision, SVD branch) and 3 x that spread is the
+    only meaningful bound."""
     worst = 0.0
     for key, val in got.items():
         exact = FX[f'{name}/c128/exact/{key}']
         scale = np.abs(exact).max()
         err = np.abs(val - exact).max() / scale
-        if dt == 'c128':
-            tol = 1e-8
-        else:
-            floor = np.abs(FX[f'{name}/c64/exact/{key}'] - exact).max() / scale
-            tol = max(1e-5, 3 * floor)
+        gap64 = np.abs(FX[f'{name}/c64/exact/{key}'] - exact).max() / scale
+        tol = 1e-7 if dt == 'c128' else max(1e-5, 3 * gap64)
+        if tie_floor:
+            spread = max(gap64, np.abs(FX[f'{name}/c128/reference/{key}'] - exact).max() / scale)
+            tol = max(tol, 3 * spread)
         print(f'{name} {dt} {key}: rel err {err:.2e} (tol {tol:.1e})')
         assert err <= tol, (name, dt, key, err, tol)
         worst = max(worst, err)
     return worst
 
 
-@pytest.mark.parametrize('dt', ['c128', 'c64'])
-def test_cfg1_full_size(cuda_prims, dt):
+def run_cfg1(dtype, tiefree):
     n, depth = 10, 10
-    dtype = C128 if dt == 'c128' else C64
     c = Simulator.TensorCircuit(qn=n, ideal=False, noiseType='idealNoise', chi=32, kappa=4, chip='medium',
                                 dtype=dtype, device='cuda:0')
+    if tiefree:
+        pre = bc.angles([7], 3 * n)
+        for q in range(n):
+            c.u3(float(pre[3 * q, 0]), float(pre[3 * q + 1, 0]), float(pre[3 * q + 2, 0]), [q], True)
     bc.brickwork(c, n, depth, bc.angles([0], bc.n_draws(n, depth, 'cz')), 'cz', prefix_ghz=True)
     st = Simulator.Tools.create_ket0Series(n, dtype=dtype, device='cpu')
     c.evolve(st)
-    compare('cfg1', gpu_quantities(c, n), dt)
+    return c, n
+
+
+@pytest.mark.parametrize('dt', ['c128', 'c64'])
+def test_cfg1_symmetry_broken(cuda_prims, dt):
+    c, n = run_cfg1(C128 if dt == 'c128' else C64, tiefree=True)
+    compare('cfg1_tiefree', gpu_quantities(c, n), dt)
+
+
+@pytest.mark.parametrize('dt', ['c128', 'c64'])
+def test_cfg1_full_size(cuda_prims, dt):
+    c, n = run_cfg1(C128 if dt == 'c128' else C64, tiefree=False)
+    compare('cfg1', gpu_quantities(c, n), dt, tie_floor=True)
 
 
 @pytest.mark.parametrize('dt', ['c128', 'c64'])

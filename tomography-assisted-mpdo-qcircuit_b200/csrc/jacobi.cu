@@ -309,6 +309,15 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
   int b = bmax < 32 ? bmax : 32;
   const int half = (n + 1) / 2;
   if (b > half) b = half;
+  if (b < half) {
+    // The matrix does not fit one CTA. A CTA's time per round grows like b^2 (b steps, each moving 2b rows
+    // through shared memory) while the number of CTAs per round is n/(2b): with few matrices in flight, small
+    // blocks spread one decomposition over many SMs (measured: b = 32 uses 2 SMs at 150 us per round for n = 128).
+    // A full batch already fills the GPU and prefers fewer, longer rounds.
+    const long long ctasAt8 = (long long)batch * ((n + 15) / 16);
+    const int target = ctasAt8 <= 2 * 148 ? 8 : (ctasAt8 <= 8 * 148 ? 16 : 32);
+    if (b > target) b = target;
+  }
   const int nb = (n + b - 1) / b;
   const int nbp = (nb + 1) & ~1;
 
