@@ -10,6 +10,8 @@
 //
 // Everything is fp64: B200 issues DFMA at half the FFMA rate, and fp64 cores make the complex64
 // path insensitive to the conditioning of the Gram matrices it feeds in here.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mpdo {
@@ -315,7 +317,8 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
     // blocks spread one decomposition over many SMs (measured: b = 32 uses 2 SMs at 150 us per round for n = 128).
     // A full batch already fills the GPU and prefers fewer, longer rounds.
     const long long ctasAt8 = (long long)batch * ((n + 15) / 16);
-    const int target = ctasAt8 <= 2 * 148 ? 8 : (ctasAt8 <= 8 * 148 ? 16 : 32);
+    int target = ctasAt8 <= 8 * 148 ? 16 : 32;   // (8 / 16 / 32 measured within noise on cfg2 and cfg3)
+    if (const char* e = getenv("MPDO_JACOBI_B")) target = atoi(e) > 0 ? atoi(e) : target;   // tuning knob
     if (b > target) b = target;
   }
   const int nb = (n + b - 1) / b;
