@@ -167,10 +167,16 @@ def main():
     ap.add_argument('--circuits', type=int, default=1024)
     ap.add_argument('--chunk', type=int, default=128)
     ap.add_argument('--out', default=None)
+    ap.add_argument('--profile', default=None, help='write a per-kernel device-time table of the run here')
     args = ap.parse_args()
     ds = lambda d: max(1, int(round(d * args.depth_scale)))
     qs = lambda q: max(4, int(round(q * args.qubit_scale)))
     lines = []
+    prof = None
+    if args.profile:
+        from torch.profiler import ProfilerActivity, profile
+        prof = profile(activities=[ProfilerActivity.CUDA])
+        prof.__enter__()
     for cfg in [int(x) for x in args.configs.split(',')]:
         torch.cuda.reset_peak_memory_stats()
         if cfg == 1:
@@ -190,6 +196,11 @@ def main():
         r['depth_scale'], r['qubit_scale'] = args.depth_scale, args.qubit_scale
         print(json.dumps(r), flush=True)
         lines.append(r)
+    if prof is not None:
+        torch.cuda.synchronize()
+        prof.__exit__(None, None, None)
+        with open(args.profile, 'w') as f:
+            f.write(prof.key_averages().table(sort_by='cuda_time_total', row_limit=20, max_name_column_width=80))
     if args.out:
         with open(args.out, 'a') as f:
             for r in lines:

@@ -117,6 +117,39 @@ int mpdo_rowscale(int batch, int rows, int cols, int vRows, const void* V, const
 int mpdo_rank_rule(int batch, int n, double* s, int sStride, int squared, int cap, double maxTruncErr,
                    int relative, int f32, int32_t* keep, int zeroTail, void* stream);
 
+/* ---- step-level entry points: one call per step of the update path (the kernel sequences of
+ * MPDOSimulator/_engine/steps.py issued from C++). Site tensors are dense row-major T[B, l, 2, a, r]; npass = 1 for
+ * complex64 states (one Gram-eig pass), 2 for complex128 (two passes + Jacobi SVD of the core). ------------------ */
+
+/* One step of the left-to-right QR sweep: Ti [B,l,2,a,r] -> Q (isometry, same shape); Tn [B,r,2,a2,r2] <- R.Tn.
+ * Replaces: tn.split_node_qr + tn.contract_between at TNNOptimizer.py:98-106 (decompositions.qr :149-195). */
+int mpdo_qr_step(int dtype, int npass, int B, int l, int a, int r, const void* Ti, int a2, int r2, const void* Tn_in,
+                 void* Q_out, void* Tn_out, void* stream);
+
+/* One step of the right-to-left bond truncation to k = min(chi, l) singular values: Tl [B,lp,2,ap,l] (left
+ * isometric), Tr [B,l,2,a,r] -> Tl.U sqrt(S) [B,lp,2,ap,k], sqrt(S) Vh [B,k,2,a,r]; sv_out (optional, [B,l] doubles)
+ * receives the singular values (their squares when npass = 1).
+ * Replaces: tn.contract_between + tn.split_node at TNNOptimizer.py:126-133 (decompositions.svd :51-146). */
+int mpdo_bond_svd_step(int dtype, int npass, int B, int lp, int ap, int l, const void* Tl, int a, int r, const void* Tr,
+                       int k, void* Tl_out, void* Tr_out, double* sv_out, void* stream);
+
+/* Inner-index truncation T [B,l,2,a,r] -> U.S [B,l,2,k,r], k = min(kappa, a); disc_out (optional, [B] doubles) = norm
+ * of the discarded part. SYNC when the top-k subspace iteration is used (a >= 64 and a >= 8k).
+ * Replaces: tn.split_node_full_svd + contract_between at TNNOptimizer.py:186-197. */
+int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const void* T, int k, void* T_out, double* disc_out,
+                        void* stream);
+
+/* Two-qubit gate absorption and split: T_lo [B,l,2,a0,m], T_hi [B,m,2,a1,r], G [Bg,2,2,2,2,K] as
+ * [p_lo,p_hi,s_lo,s_hi,g] (Bg = 1 or B, same dtype as the state) -> T_lo' [B,l,2,a0,k], T_hi' [B,k,2,K*a1,r] with the
+ * kept rank k from the reference rule ||s|| - ||s[:k]|| <= max_err. The rank is data dependent: `alloc(which, count,
+ * user)` is called once it is known and returns device memory for `count` complex elements (which = 0: T_lo',
+ * 1: T_hi'). SYNC (rank read-back).
+ * Replaces: tn.contractors.optimal + tn.flatten_edges + tn.split_node at Circuit.py:104-124. */
+typedef void* (*mpdo_alloc_fn)(int which, int64_t count, void* user);
+int mpdo_split_2q(int dtype, int npass, int B, int l, int a0, int m, const void* Tlo, int a1, int r, const void* Thi,
+                  int Bg, int K, const void* G, double max_err, mpdo_alloc_fn alloc, void* user, int* k_out,
+                  void* stream);
+
 /* Elementwise dtype conversion between complex64 and complex128 (count complex elements). */
 int mpdo_cast(int dtypeIn, int dtypeOut, int64_t count, const void* in, void* out, void* stream);
 

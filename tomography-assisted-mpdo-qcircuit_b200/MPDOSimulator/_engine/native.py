@@ -1,0 +1,87 @@
+"""The production engine: each step of the update path is ONE call into libmpdo_b200.so
+(mpdo_split_2q, mpdo_qr_step, mpdo_bond_svd_step, mpdo_kappa_truncate; csrc/engine.cu issues the same kernel
+sequences that steps.Engine spells out over the Python primitive wrappers). steps.Engine stays the readable
+statement of the algorithm, the path for the rarely used relative-error truncation rule, and what the CPU tier
+exercises against the oracle; NativeEngine only removes ~50 Python-level launches per step from the hot loop."""
+import ctypes as C
+
+import torch
+
+from . import lib as _lib
+from .steps import Engine
+
+_DT = {torch.complex64: _lib.MPDO_C64, torch.complex128: _lib.MPDO_C128}
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_int, C.c_int64, C.c_void_p)
+
+
+def _stream():
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch.cuda.current_device()))
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class NativeEngine(Engine):
+    def __init__(self, prims, dtype, npass=None):
+        super().__init__(prims, dtype, npass)
+        self.lib = _lib.load()
+        self.dt = _DT[dtype]
+
+    def qr_step(self, Ti, Tn):
+        Ti, Tn = Ti.contiguous(), Tn.contiguous()
+        Bn, l, _, a, r = Ti.shape
+        _, _, _, a2, r2 = Tn.shape
+        Q, Tn_new = torch.empty_like(Ti), torch.empty_like(Tn)
+        _lib.check(self.lib.mpdo_qr_step(self.dt, self.npass, Bn, l, a, r, _p(Ti), a2, r2, _p(Tn), _p(Q), _p(Tn_new),
+                                         _stream()), 'mpdo_qr_step')
+        return Q, Tn_new
+
+    def bond_svd_step(self, Tl, Tr, chi, max_err=None):
+        if max_err is not None:
+            return super().bond_svd_step(Tl, Tr, chi, max_err)
+        Tl, Tr = Tl.contiguous(), Tr.contiguous()
+        Bn, lp, _, ap, l = Tl.shape
+        _, _, _, a, r = Tr.shape
+        k = l if chi is None else min(int(chi), l)
+        Tl_n = torch.empty((Bn, lp, 2, ap, k), dtype=Tl.dtype, device=Tl.device)
+        Tr_n = torch.empty((Bn, k, 2, a, r), dtype=Tr.dtype, device=Tr.device)
+        sv = torch.empty((Bn, l), dtype=torch.float64, device=Tr.device)
+        _lib.check(self.lib.mpdo_bond_svd_step(self.dt, self.npass, Bn, lp, ap, l, _p(Tl), a, r, _p(Tr), k, _p(Tl_n),
+                                               _p(Tr_n), _p(sv), _stream()), 'mpdo_bond_svd_step')
+        disc = sv[:, k:].clamp_min(0).sqrt() if self.npass == 1 else sv[:, k:]
+        return Tl_n, Tr_n, disc
+
+    def kappa_truncate(self, T, kappa, max_err=None):
+        if max_err is not None or kappa is None:
+            return super().kappa_truncate(T, kappa, max_err)
+        T = T.contiguous()
+        Bn, l, _, a, r = T.shape
+        k = min(int(kappa), a)
+        T_n = torch.empty((Bn, l, 2, k, r), dtype=T.dtype, device=T.device)
+        disc = torch.empty((Bn,), dtype=torch.float64, device=T.device)
+        _lib.check(self.lib.mpdo_kappa_truncate(self.dt, Bn, l, a, r, _p(T), k, _p(T_n), _p(disc), _stream()),
+                   'mpdo_kappa_truncate')
+        return T_n, disc.unsqueeze(1)
+
+    def split_2q(self, Tlo, Thi, G, max_err=2.718281828459045e-8):
+        Tlo, Thi, G = Tlo.contiguous(), Thi.contiguous(), G.contiguous()
+        Bn, l, _, a0, m = Tlo.shape
+        _, _, _, a1, r = Thi.shape
+        Bg, K = G.shape[0], G.shape[-1]
+        assert G.dtype == Tlo.dtype == Thi.dtype
+        outs = {}
+
+        def alloc(which, count, _user):
+            t = torch.empty(int(count), dtype=Tlo.dtype, device=Tlo.device)
+            outs[which] = t
+            return t.data_ptr()
+
+        cb = ALLOC_FN(alloc)
+        k = C.c_int(0)
+        _lib.check(self.lib.mpdo_split_2q(self.dt, self.npass, Bn, l, a0, m, _p(Tlo), a1, r, _p(Thi), Bg, K, _p(G),
+                                          -1.0 if max_err is None else float(max_err), cb, None, C.byref(k),
+                                          _stream()), 'mpdo_split_2q')
+        kk = k.value
+        self.stats['last_rank'] = kk
+        return outs[0].view(Bn, l, 2, a0, kk), outs[1].view(Bn, kk, 2, K * a1, r)

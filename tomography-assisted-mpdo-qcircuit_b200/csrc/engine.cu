@@ -1,0 +1,731 @@
+// Native engine of the MPDO update path: the kernel sequences of one gate split, one QR-sweep step, one
+// chi-truncation step and one kappa truncation, issued from C++ on the caller's stream.
+//
+// The reference runs these steps through tensornetwork + LAPACK (Circuit.py:74-136, TNNOptimizer.py:87-197);
+// MPDOSimulator/_engine/steps.py states the same sequences over the Python primitive wrappers and documents the
+// mathematics (Gram-eig orthogonalisation, isometry shortcut, core split, top-kappa subspace iteration). This file
+// is the production path: one C call per step instead of ~50 Python-level launches, which is what bounds a layer
+// once the kernels themselves take tens of microseconds.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "engine.cuh"
+
+namespace mpdo {
+namespace eng {
+
+// ---------------------------------------------------------------------------------------------------
+// contraction descriptor from strided views (port of prims.py:_levels/_idxmap)
+// ---------------------------------------------------------------------------------------------------
+struct Level {
+  long long n, s;
+};
+
+static int collapse(const Tn& t, int d0, int cnt, Level* lv) {
+  int k = 0;
+  for (int d = d0; d < d0 + cnt; ++d) {
+    long long n = t.sh[d], s = t.st[d];
+    if (n == 1) continue;
+    if (k > 0 && lv[k - 1].s == s * n) {
+      lv[k - 1].n *= n;
+      lv[k - 1].s = s;
+    } else {
+      lv[k].n = n;
+      lv[k].s = s;
+      ++k;
+    }
+  }
+  return k;
+}
+
+static bool to_map(const Level* lv, int k, mpdo_idxmap* m) {
+  memset(m, 0, sizeof(*m));
+  if (k == 0) return true;
+  if (k == 1) {
+    m->s0 = lv[0].s;
+  } else if (k == 2) {
+    m->d0 = (int)lv[1].n;
+    m->s0 = lv[1].s;
+    m->s1 = lv[0].s;
+  } else if (k == 3) {
+    m->d0 = (int)lv[2].n;
+    m->d1 = (int)lv[1].n;
+    m->s0 = lv[2].s;
+    m->s1 = lv[1].s;
+    m->s2 = lv[0].s;
+  } else {
+    return false;
+  }
+  return true;
+}
+
+static long long prod(const Tn& t, int d0, int cnt) {
+  long long p = 1;
+  for (int d = d0; d < d0 + cnt; ++d) p *= t.sh[d];
+  return p;
+}
+
+static int sm_count() {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+int contract(cudaStream_t st, const Tn& A, Roles ra, const Tn& B, Roles rb, const Tn& C, Roles rc, bool conjA,
+             bool conjB, int acc64, double alpha, double beta) {
+  mpdo_contract_desc d;
+  memset(&d, 0, sizeof(d));
+  const long long M = prod(A, ra.nb, ra.n1), K = prod(A, ra.nb + ra.n1, ra.n2);
+  const long long N = prod(B, rb.nb + rb.n1, rb.n2), batch = prod(A, 0, ra.nb);
+  if (prod(B, rb.nb, rb.n1) != K || prod(C, rc.nb, rc.n1) != M || prod(C, rc.nb + rc.n1, rc.n2) != N ||
+      prod(B, 0, rb.nb) != batch || prod(C, 0, rc.nb) != batch)
+    return fail(MPDO_EINVAL, "engine contract: inconsistent extents");
+  d.M = (int)M;
+  d.N = (int)N;
+  d.K = (int)K;
+  d.batch = (int)batch;
+  d.dtypeA = A.dt;
+  d.dtypeB = B.dt;
+  d.dtypeC = C.dt;
+  d.conjA = conjA;
+  d.conjB = conjB;
+  const bool all64 = A.dt == MPDO_C64 && B.dt == MPDO_C64 && C.dt == MPDO_C64;
+  d.acc64 = acc64 >= 0 ? acc64 : !all64;
+  Level lab[MAXD], lai[MAXD], lak[MAXD], lbb[MAXD], lbk[MAXD], lbj[MAXD], lcb[MAXD], lci[MAXD], lcj[MAXD];
+  const int nab = collapse(A, 0, ra.nb, lab), nai = collapse(A, ra.nb, ra.n1, lai),
+            nak = collapse(A, ra.nb + ra.n1, ra.n2, lak);
+  const int nbb = collapse(B, 0, rb.nb, lbb), nbk = collapse(B, rb.nb, rb.n1, lbk),
+            nbj = collapse(B, rb.nb + rb.n1, rb.n2, lbj);
+  const int ncb = collapse(C, 0, rc.nb, lcb), nci = collapse(C, rc.nb, rc.n1, lci),
+            ncj = collapse(C, rc.nb + rc.n1, rc.n2, lcj);
+  if (!to_map(lab, nab, &d.Ab) || !to_map(lai, nai, &d.Ai) || !to_map(lak, nak, &d.Ak) || !to_map(lbb, nbb, &d.Bb) ||
+      !to_map(lbk, nbk, &d.Bk) || !to_map(lbj, nbj, &d.Bj) || !to_map(lcb, ncb, &d.Cb) || !to_map(lci, nci, &d.Ci) ||
+      !to_map(lcj, ncj, &d.Cj))
+    return fail(MPDO_EINVAL, "engine contract: an axis group needs more than 3 stride levels");
+  auto inner = [](const Level* lv, int k) { return k ? lv[k - 1].s : (1LL << 60); };
+  d.a_kfast = inner(lak, nak) <= inner(lai, nai);
+  d.b_jfast = inner(lbj, nbj) <= inner(lbk, nbk);
+  const long long tiles = ((M + 63) / 64) * ((N + 63) / 64) * batch;
+  int ksplit = 1;
+  const int sms = sm_count();
+  if (K >= 1024 && tiles < 2 * sms && C.contiguous() && (beta == 0.0 || beta == 1.0))
+    ksplit = (int)std::max(1LL, std::min((K + 255) / 256, (4LL * sms) / std::max(tiles, 1LL)));
+  d.ksplit = ksplit;
+  d.alpha = alpha;
+  d.beta = beta;
+  if (ksplit > 1 && beta == 0.0) MPDO_CUDA(cudaMemsetAsync(C.p, 0, (size_t)C.numel() * C.esz(), st));
+  return mpdo_contract(&d, A.p, B.p, C.p, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// strided copy with dtype conversion / conjugation (permutes and casts that torch did in the Python engine)
+// ---------------------------------------------------------------------------------------------------
+struct CopyArgs {
+  int nd;
+  long long sh[MAXD], st[MAXD];
+};
+
+template <typename CI, typename CO>
+__global__ void __launch_bounds__(256) copy_view_kernel(CopyArgs a, long long total, const CI* __restrict__ in,
+                                                        CO* __restrict__ out, int conj) {
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long rem = idx, off = 0;
+    for (int d = a.nd - 1; d >= 0; --d) {
+      const long long c = rem % a.sh[d];
+      rem /= a.sh[d];
+      off += c * a.st[d];
+    }
+    CI v = in[off];
+    CO o = cconv<CO>(v);
+    if (conj) o.y = -o.y;
+    out[idx] = o;
+  }
+}
+
+static int copy_view(cudaStream_t st, const Tn& in, const Tn& out, bool conj = false) {  // out contiguous
+  CopyArgs a;
+  a.nd = in.nd;
+  for (int i = 0; i < in.nd; ++i) {
+    a.sh[i] = in.sh[i];
+    a.st[i] = in.st[i];
+  }
+  const long long total = in.numel();
+  if (total == 0) return 0;
+  unsigned gx = (unsigned)std::min<long long>((total + 255) / 256, 148 * 16);
+  if (in.dt == MPDO_C64 && out.dt == MPDO_C64)
+    copy_view_kernel<float2, float2><<<gx, 256, 0, st>>>(a, total, (const float2*)in.p, (float2*)out.p, conj);
+  else if (in.dt == MPDO_C64)
+    copy_view_kernel<float2, double2><<<gx, 256, 0, st>>>(a, total, (const float2*)in.p, (double2*)out.p, conj);
+  else if (out.dt == MPDO_C64)
+    copy_view_kernel<double2, float2><<<gx, 256, 0, st>>>(a, total, (const double2*)in.p, (float2*)out.p, conj);
+  else
+    copy_view_kernel<double2, double2><<<gx, 256, 0, st>>>(a, total, (const double2*)in.p, (double2*)out.p, conj);
+  return check_launch("copy_view_kernel");
+}
+
+// residual norms of the kept Ritz pairs, relative to the leading Ritz value: out[b] = max_j |R[b,j,:]| / theta[b,0]
+__global__ void __launch_bounds__(256) residual_kernel(int k, int n, const double2* __restrict__ R,
+                                                       const double* __restrict__ theta, int thetaStride,
+                                                       double* __restrict__ out) {
+  __shared__ double red[8];
+  const int b = blockIdx.x;
+  double worst = 0;
+  for (int j = 0; j < k; ++j) {
+    const double2* row = R + ((long long)b * k + j) * n;
+    double a = 0;
+    for (int c = threadIdx.x; c < n; c += blockDim.x) a = fma(row[c].x, row[c].x, fma(row[c].y, row[c].y, a));
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+      worst = fmax(worst, sqrt(s));
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[b] = worst / fmax(theta[(long long)b * thetaStride], 1e-300);
+}
+
+// trace of G minus the kept eigenvalues -> norm of the discarded part (diagnostic output of the kappa step)
+__global__ void discarded_kernel(int B, int n, int k, const double2* __restrict__ G, const double* __restrict__ theta,
+                                 int thetaStride, double* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double tr = 0;
+  for (int i = 0; i < n; ++i) tr += G[((long long)b * n + i) * n + i].x;
+  for (int j = 0; j < k; ++j) tr -= theta[(long long)b * thetaStride + j];
+  out[b] = sqrt(fmax(tr, 0.0));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// engine context and small-core helpers
+// ---------------------------------------------------------------------------------------------------
+struct Ctx {
+  cudaStream_t st;
+  Arena ar;
+  int dt;      // dtype of the state tensors
+  bool f32;
+  int npass;   // 1: Gram-eig once (complex64), 2: twice + Jacobi SVD of the core (complex128)
+  double null_tol = 1e-14, floor_tol = 1e-13, jtol = 1e-15;
+  Ctx(cudaStream_t s, int dtype, int np) : st(s), ar(s), dt(dtype), f32(dtype == MPDO_C64), npass(np) {}
+};
+
+#define EC(call)            \
+  do {                      \
+    int rc_ = (call);       \
+    if (rc_ != 0) return rc_; \
+  } while (0)
+#define ARENA_OK(c)                  \
+  do {                               \
+    if ((c).ar.err) return (c).ar.err; \
+  } while (0)
+
+static int decompose(Ctx& c, const Tn& L, bool wantRows, double** s, Tn* Yn, Tn* Z) {
+  const long long B = L.sh[0], n = L.sh[1], m = L.sh[2];
+  Tn Y = c.ar.alloc(MPDO_C128, {B, n, m + n});
+  int32_t* work = (int32_t*)c.ar.raw(sizeof(int32_t) * 48 * (size_t)B);
+  *s = c.ar.reals(B * n);
+  *Z = c.ar.alloc(MPDO_C128, {B, n, n});
+  if (wantRows) *Yn = c.ar.alloc(MPDO_C128, {B, n, m});
+  ARENA_OK(c);
+  const double tol = std::max(c.jtol, 4.4e-16 * sqrt((double)m));
+  return mpdo_decompose_rows((int)B, (int)n, (int)m, L.p, Y.p, work, *s, wantRows ? Yn->p : nullptr, Z->p,
+                             wantRows ? 1 : 0, wantRows ? 1e-300 : 0.0, tol, 30, c.st);
+}
+
+// G = Vh^h diag(lam) Vh (Hermitian PSD, complex128 contiguous [B,n,n])
+static int eigh(Ctx& c, const Tn& G, double** lam, Tn* Vh) {
+  Tn none;
+  return decompose(c, G, false, lam, &none, Vh);
+}
+
+static int rowscale(Ctx& c, const Tn& V, const double* lam, int lamStride, int rows, double power, double tol, int mode,
+                    int dtX, Tn* X) {
+  const long long B = V.sh[0], vrows = V.sh[1], cols = V.sh[2];
+  *X = c.ar.alloc(dtX, {B, (long long)rows, cols});
+  ARENA_OK(c);
+  return mpdo_rowscale((int)B, rows, (int)cols, (int)vrows, V.p, lam, lamStride, power, tol, mode, dtX, X->p, c.st);
+}
+
+// kept rank (batch maximum) by the reference rule; zero-tails sv in place. SYNC when max_err >= 0.
+static int keep_rank(Ctx& c, double* sv, int B, int n, bool squared, int cap, double max_err, bool relative, int* k) {
+  if (cap < 0 || cap > n) cap = n;
+  if (max_err < 0) {
+    *k = cap;
+    return 0;
+  }
+  int32_t* dk = (int32_t*)c.ar.raw(sizeof(int32_t) * (size_t)B);
+  ARENA_OK(c);
+  EC(mpdo_rank_rule(B, n, sv, n, squared, cap, max_err, relative, c.f32, dk, 1, c.st));
+  static thread_local int32_t* hk = nullptr;
+  static thread_local int hcap = 0;
+  if (hcap < B) {
+    if (hk) cudaFreeHost(hk);
+    MPDO_CUDA(cudaMallocHost(&hk, sizeof(int32_t) * (size_t)B));
+    hcap = B;
+  }
+  MPDO_CUDA(cudaMemcpyAsync(hk, dk, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, c.st));
+  MPDO_CUDA(cudaStreamSynchronize(c.st));
+  int best = 1;
+  for (int i = 0; i < B; ++i) best = std::max(best, (int)hk[i]);
+  *k = best;
+  return 0;
+}
+
+// views with the two matrix axes swapped: [b.. | rows.. | cols..] -> [b.. | cols.. | rows..]
+static Tn swap_groups(const Tn& X, Roles r) {
+  Tn t = X;
+  int pos = r.nb;
+  for (int d = 0; d < r.n2; ++d, ++pos) {
+    t.sh[pos] = X.sh[r.nb + r.n1 + d];
+    t.st[pos] = X.st[r.nb + r.n1 + d];
+  }
+  for (int d = 0; d < r.n1; ++d, ++pos) {
+    t.sh[pos] = X.sh[r.nb + d];
+    t.st[pos] = X.st[r.nb + d];
+  }
+  return t;
+}
+
+static Tn like_contig(Ctx& c, const Tn& X, int dt) {  // fresh contiguous tensor with X's logical shape
+  Tn t;
+  t.dt = dt;
+  t.nd = X.nd;
+  long long s = 1;
+  for (int d = X.nd - 1; d >= 0; --d) {
+    t.sh[d] = X.sh[d];
+    t.st[d] = s;
+    s *= X.sh[d];
+  }
+  t.p = (char*)c.ar.raw((size_t)s * t.esz());
+  return t;
+}
+
+// G[b,c,c'] = sum_rows conj(X[b,rows,c]) X[b,rows,c']
+static int gram_cols(Ctx& c, const Tn& X, Roles r, Tn* G) {
+  const long long B = prod(X, 0, r.nb), n = prod(X, r.nb + r.n1, r.n2);
+  *G = c.ar.alloc(MPDO_C128, {B, n, n});
+  ARENA_OK(c);
+  return contract(c.st, swap_groups(X, r), {r.nb, r.n2, r.n1}, X, r, *G, {1, 1, 1}, true, false, 1);
+}
+
+// G[b,i,i'] = sum_cols M[b,i,cols] conj(M[b,i',cols])
+static int gram_rows(Ctx& c, const Tn& M, Roles r, Tn* G) {
+  const long long B = prod(M, 0, r.nb), n = prod(M, r.nb, r.n1);
+  *G = c.ar.alloc(MPDO_C128, {B, n, n});
+  ARENA_OK(c);
+  return contract(c.st, M, r, swap_groups(M, r), {r.nb, r.n2, r.n1}, *G, {1, 1, 1}, false, true, 1);
+}
+
+static Tn transposed(const Tn& X) { return X.permute({0, 2, 1}); }  // [B,a,b] -> [B,b,a] view
+
+// Tall view X -> Q = Alast . Xs^h (isometry, zero columns for null directions), X = Q . R
+static int orth_cols(Ctx& c, const Tn& X, Roles r, Tn* Alast, Tn* Xs, Tn* R) {
+  Tn G, Vh;
+  double* lam;
+  EC(gram_cols(c, X, r, &G));
+  EC(eigh(c, G, &lam, &Vh));
+  const int n = (int)G.sh[1];
+  if (c.npass == 1) {
+    EC(rowscale(c, Vh, lam, n, n, -0.5, c.null_tol, 0, MPDO_C128, Xs));
+    EC(rowscale(c, Vh, lam, n, n, 0.5, c.null_tol, 0, MPDO_C128, R));
+    *Alast = X;
+    return 0;
+  }
+  Tn Xs1, R1, G2, Vh2, R2;
+  double* lam2;
+  EC(rowscale(c, Vh, lam, n, n, -0.5, c.floor_tol, 1, MPDO_C128, &Xs1));
+  EC(rowscale(c, Vh, lam, n, n, 0.5, c.floor_tol, 1, MPDO_C128, &R1));
+  Tn A1 = like_contig(c, X, c.dt);
+  ARENA_OK(c);
+  EC(contract(c.st, X, r, transposed(Xs1), {1, 1, 1}, A1, r, false, true));
+  EC(gram_cols(c, A1, r, &G2));
+  EC(eigh(c, G2, &lam2, &Vh2));
+  EC(rowscale(c, Vh2, lam2, n, n, -0.5, c.null_tol, 0, MPDO_C128, Xs));
+  EC(rowscale(c, Vh2, lam2, n, n, 0.5, c.null_tol, 0, MPDO_C128, &R2));
+  *R = c.ar.alloc(MPDO_C128, {G.sh[0], (long long)n, (long long)n});
+  ARENA_OK(c);
+  EC(contract(c.st, R2, {1, 1, 1}, R1, {1, 1, 1}, *R, {1, 1, 1}));
+  *Alast = A1;
+  return 0;
+}
+
+// Wide view M -> Qt = F . Mlast (orthonormal or zero rows), M = Lh^h . Qt
+static int orth_rows(Ctx& c, const Tn& M, Roles r, Tn* Mlast, Tn* F, Tn* Lh, double** lam_out = nullptr,
+                     Tn* Uh_out = nullptr) {
+  Tn G, Uh;
+  double* lam;
+  EC(gram_rows(c, M, r, &G));
+  EC(eigh(c, G, &lam, &Uh));
+  const int n = (int)G.sh[1];
+  if (lam_out) *lam_out = lam;
+  if (Uh_out) *Uh_out = Uh;
+  if (c.npass == 1) {
+    EC(rowscale(c, Uh, lam, n, n, -0.5, c.null_tol, 0, MPDO_C128, F));
+    EC(rowscale(c, Uh, lam, n, n, 0.5, c.null_tol, 0, MPDO_C128, Lh));
+    *Mlast = M;
+    return 0;
+  }
+  Tn F1, R1, G2, Uh2, R2;
+  double* lam2;
+  EC(rowscale(c, Uh, lam, n, n, -0.5, c.floor_tol, 1, MPDO_C128, &F1));
+  EC(rowscale(c, Uh, lam, n, n, 0.5, c.floor_tol, 1, MPDO_C128, &R1));
+  Tn M1 = like_contig(c, M, c.dt);
+  ARENA_OK(c);
+  EC(contract(c.st, F1, {1, 1, 1}, M, r, M1, r));
+  EC(gram_rows(c, M1, r, &G2));
+  EC(eigh(c, G2, &lam2, &Uh2));
+  EC(rowscale(c, Uh2, lam2, n, n, -0.5, c.null_tol, 0, MPDO_C128, F));
+  EC(rowscale(c, Uh2, lam2, n, n, 0.5, c.null_tol, 0, MPDO_C128, &R2));
+  *Lh = c.ar.alloc(MPDO_C128, {G.sh[0], (long long)n, (long long)n});
+  ARENA_OK(c);
+  EC(contract(c.st, R2, {1, 1, 1}, R1, {1, 1, 1}, *Lh, {1, 1, 1}));
+  *Mlast = M1;
+  return 0;
+}
+
+// Truncatable SVD of a wide view M = U diag(s) Vh: singular values (squared in one-pass mode) and, once the kept
+// rank k is known, right(k) with sqrt(S_k) Vh_k = right . Mlast and left(k)[j,i] = sqrt(s_j) conj(U[i,j]).
+struct WideSvd {
+  Tn Mlast, Uh, Wh, F;  // one pass: Uh (eigenvectors); two passes: Uh = left vectors, Wh, F
+  double* sv = nullptr;
+  bool squared = false;
+  int n = 0;
+};
+
+static int svd_wide(Ctx& c, const Tn& M, Roles r, WideSvd* w) {
+  if (c.npass == 1) {
+    Tn G;
+    EC(gram_rows(c, M, r, &G));
+    EC(eigh(c, G, &w->sv, &w->Uh));
+    w->Mlast = M;
+    w->squared = true;
+    w->n = (int)G.sh[1];
+    return 0;
+  }
+  Tn Lh, Uh_, Wh_;
+  EC(orth_rows(c, M, r, &w->Mlast, &w->F, &Lh));
+  EC(decompose(c, Lh, true, &w->sv, &Wh_, &Uh_));  // Lh = Uh_^h diag(s) Wh_  ->  L = Lh^h = Wh_^h diag(s) Uh_
+  w->Uh = Wh_;                                     // Uh_L
+  w->Wh = Uh_;                                     // Wh_L
+  w->squared = false;
+  w->n = (int)Lh.sh[1];
+  return 0;
+}
+
+static int wide_right(Ctx& c, const WideSvd& w, int k, int dt, Tn* out) {
+  if (c.npass == 1) return rowscale(c, w.Uh, w.sv, w.n, k, -0.25, c.null_tol, 0, dt, out);
+  Tn ws;
+  EC(rowscale(c, w.Wh, w.sv, w.n, k, 0.5, 0.0, 0, MPDO_C128, &ws));
+  *out = c.ar.alloc(dt, {w.F.sh[0], (long long)k, w.F.sh[2]});
+  ARENA_OK(c);
+  return contract(c.st, ws, {1, 1, 1}, w.F, {1, 1, 1}, *out, {1, 1, 1});
+}
+
+static int wide_left(Ctx& c, const WideSvd& w, int k, int dt, Tn* out) {
+  if (c.npass == 1) return rowscale(c, w.Uh, w.sv, w.n, k, 0.25, c.null_tol, 0, dt, out);
+  return rowscale(c, w.Uh, w.sv, w.n, k, 0.5, 0.0, 0, dt, out);
+}
+
+// Leading k eigenpairs of Hermitian PSD G by block subspace iteration with Rayleigh-Ritz, run to residual
+// convergence (steps.py: Engine.eigh_topk). Vt[b,j,:] = components of eigenvector j. converged = 0 -> caller
+// falls back to the full decomposition.
+static int eigh_topk(Ctx& c, const Tn& G, int k, double** theta_out, Tn* Vt, int* converged) {
+  const long long B = G.sh[0], n = G.sh[1];
+  const int blk = (int)std::min<long long>(n, std::max(2 * k, k + 28));
+  const double tol = c.f32 ? 1e-10 : 1e-12;
+  // deterministic start block (a fixed pseudo-random pattern; any generic block works)
+  std::vector<double> host((size_t)blk * n * 2);
+  unsigned long long sd = 0x9E3779B97F4A7C15ULL;
+  for (size_t i = 0; i < host.size(); ++i) {
+    sd ^= sd << 13;
+    sd ^= sd >> 7;
+    sd ^= sd << 17;
+    host[i] = ((double)(sd >> 11) / 9007199254740992.0) * 2.0 - 1.0;
+  }
+  Tn om = c.ar.alloc(MPDO_C128, {1, (long long)blk, n});
+  ARENA_OK(c);
+  MPDO_CUDA(cudaMemcpyAsync(om.p, host.data(), host.size() * sizeof(double), cudaMemcpyHostToDevice, c.st));
+  MPDO_CUDA(cudaStreamSynchronize(c.st));  // `host` goes out of scope below; the copy is tiny
+  Tn Yr = om.expand(0, B);
+  Tn Gt = transposed(G);
+  Tn Zr = c.ar.alloc(MPDO_C128, {B, (long long)blk, n});
+  double* res = c.ar.reals(B);
+  ARENA_OK(c);
+  EC(contract(c.st, Yr, {1, 1, 1}, Gt, {1, 1, 1}, Zr, {1, 1, 1}));
+  static thread_local double* hres = nullptr;
+  static thread_local long long hcap = 0;
+  if (hcap < B) {
+    if (hres) cudaFreeHost(hres);
+    MPDO_CUDA(cudaMallocHost(&hres, sizeof(double) * (size_t)B));
+    hcap = B;
+  }
+  *converged = 0;
+  for (int it = 0; it < 40; ++it) {
+    Tn H, Uh, Fo, Bm, Wh, ts;
+    double *lam, *theta;
+    EC(gram_rows(c, Zr, {1, 1, 1}, &H));
+    EC(eigh(c, H, &lam, &Uh));
+    EC(rowscale(c, Uh, lam, blk, blk, -0.5, c.null_tol, 0, MPDO_C128, &Fo));
+    Tn Y2 = c.ar.alloc(MPDO_C128, {B, (long long)blk, n});
+    Tn Z2 = c.ar.alloc(MPDO_C128, {B, (long long)blk, n});
+    Bm = c.ar.alloc(MPDO_C128, {B, (long long)blk, (long long)blk});
+    ARENA_OK(c);
+    EC(contract(c.st, Fo, {1, 1, 1}, Zr, {1, 1, 1}, Y2, {1, 1, 1}));
+    EC(contract(c.st, Y2, {1, 1, 1}, Gt, {1, 1, 1}, Z2, {1, 1, 1}));
+    EC(contract(c.st, Z2, {1, 1, 1}, transposed(Y2), {1, 1, 1}, Bm, {1, 1, 1}, false, true));
+    EC(eigh(c, Bm, &theta, &Wh));
+    Tn Y3 = c.ar.alloc(MPDO_C128, {B, (long long)blk, n});
+    Tn Z3 = c.ar.alloc(MPDO_C128, {B, (long long)blk, n});
+    ARENA_OK(c);
+    EC(contract(c.st, Wh, {1, 1, 1}, Y2, {1, 1, 1}, Y3, {1, 1, 1}));
+    EC(contract(c.st, Wh, {1, 1, 1}, Z2, {1, 1, 1}, Z3, {1, 1, 1}));
+    // residual rows R = Z3[:k] - theta * Y3[:k]  (scale Wh[:k] by theta, multiply by Y2, subtract from Wh[:k] Z2)
+    Tn Rr = c.ar.alloc(MPDO_C128, {B, (long long)k, n});
+    ARENA_OK(c);
+    EC(rowscale(c, Wh, theta, blk, k, 1.0, 0.0, 0, MPDO_C128, &ts));
+    EC(contract(c.st, Wh.narrow(1, 0, k), {1, 1, 1}, Z2, {1, 1, 1}, Rr, {1, 1, 1}));
+    EC(contract(c.st, ts, {1, 1, 1}, Y2, {1, 1, 1}, Rr, {1, 1, 1}, false, false, -1, -1.0, 1.0));
+    residual_kernel<<<(unsigned)B, 256, 0, c.st>>>(k, (int)n, (const double2*)Rr.p, theta, blk, res);
+    EC(check_launch("residual_kernel"));
+    MPDO_CUDA(cudaMemcpyAsync(hres, res, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c.st));
+    MPDO_CUDA(cudaStreamSynchronize(c.st));
+    double worst = 0;
+    for (long long i = 0; i < B; ++i) worst = std::max(worst, hres[i]);
+    Yr = Y3;
+    Zr = Z3;
+    if (worst <= tol) {
+      *converged = 1;
+      *theta_out = theta;   // stride blk
+      *Vt = Y3;             // [B, blk, n]; the first k rows are the kept vectors
+      return 0;
+    }
+  }
+  return 0;
+}
+
+}  // namespace eng
+}  // namespace mpdo
+
+using namespace mpdo;
+using namespace mpdo::eng;
+
+// ===================================================================================================
+// C entry points
+// ===================================================================================================
+
+extern "C" int mpdo_qr_step(int dtype, int npass, int B, int l, int a, int r, const void* Ti, int a2, int r2,
+                            const void* Tn_in, void* Q_out, void* Tn_out, void* stream) {
+  Ctx c((cudaStream_t)stream, dtype, npass);
+  Tn T = Tn::contig((void*)Ti, dtype, {B, l, 2, a, r});
+  Tn Tnx = Tn::contig((void*)Tn_in, dtype, {B, r, 2, a2, r2});
+  Tn Q = Tn::contig(Q_out, dtype, {B, l, 2, a, r});
+  Tn To = Tn::contig(Tn_out, dtype, {B, r, 2, a2, r2});
+  Tn Alast, Xs, R, Xsd, Rd;
+  EC(orth_cols(c, T, {1, 3, 1}, &Alast, &Xs, &R));
+  Xsd = c.ar.alloc(dtype, {B, r, r});
+  Rd = c.ar.alloc(dtype, {B, r, r});
+  ARENA_OK(c);
+  EC(copy_view(c.st, Xs, Xsd));
+  EC(copy_view(c.st, R, Rd));
+  EC(contract(c.st, Alast, {1, 3, 1}, transposed(Xsd), {1, 1, 1}, Q, {1, 3, 1}, false, true));
+  return contract(c.st, Rd, {1, 1, 1}, Tnx, {1, 1, 3}, To, {1, 1, 3});
+}
+
+// chi truncation step without the relative-error rule: k = min(chi, l). Tl [B,lp,2,ap,l], Tr [B,l,2,a,r].
+extern "C" int mpdo_bond_svd_step(int dtype, int npass, int B, int lp, int ap, int l, const void* Tl, int a, int r,
+                                  const void* Tr, int k, void* Tl_out, void* Tr_out, double* disc_out, void* stream) {
+  Ctx c((cudaStream_t)stream, dtype, npass);
+  Tn TL = Tn::contig((void*)Tl, dtype, {B, lp, 2, ap, l});
+  Tn TR = Tn::contig((void*)Tr, dtype, {B, l, 2, a, r});
+  Tn TLo = Tn::contig(Tl_out, dtype, {B, lp, 2, ap, k});
+  Tn TRo = Tn::contig(Tr_out, dtype, {B, k, 2, a, r});
+  WideSvd w;
+  EC(svd_wide(c, TR, {1, 1, 3}, &w));
+  if (disc_out)  // singular values (squared in one-pass mode), all l of them, for the caller's truncation record
+    MPDO_CUDA(cudaMemcpyAsync(disc_out, w.sv, sizeof(double) * (size_t)B * w.n, cudaMemcpyDeviceToDevice, c.st));
+  Tn right, left;
+  EC(wide_right(c, w, k, dtype, &right));
+  EC(contract(c.st, right, {1, 1, 1}, w.Mlast, {1, 1, 3}, TRo, {1, 1, 3}));
+  EC(wide_left(c, w, k, dtype, &left));
+  return contract(c.st, TL, {1, 3, 1}, transposed(left), {1, 1, 1}, TLo, {1, 3, 1}, false, true);
+}
+
+// kappa truncation without the relative-error rule: k = min(kappa, a). disc_out[b] = norm of the discarded part.
+extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const void* T, int k, void* T_out,
+                                   double* disc_out, void* stream) {
+  Ctx c((cudaStream_t)stream, dtype, 1);
+  Tn Tv = Tn::contig((void*)T, dtype, {B, l, 2, a, r});
+  Tn To = Tn::contig(T_out, dtype, {B, l, 2, k, r});
+  Tn G;
+  EC(gram_cols(c, Tv.permute({0, 1, 2, 4, 3}), {1, 3, 1}, &G));
+  Tn Tperm = Tv.permute({0, 3, 1, 2, 4});   // [b | a | l,s,r]
+  Tn Operm = To.permute({0, 3, 1, 2, 4});   // [b | k | l,s,r]
+  double* theta = nullptr;
+  int thetaStride = a;
+  bool done = false;
+  if (a >= 64 && a >= 8 * k) {
+    Tn Vt;
+    int conv = 0;
+    EC(eigh_topk(c, G, k, &theta, &Vt, &conv));
+    if (conv) {
+      thetaStride = (int)Vt.sh[1];
+      Tn Vk = c.ar.alloc(dtype, {(long long)B, (long long)k, (long long)a});
+      ARENA_OK(c);
+      EC(copy_view(c.st, Vt.narrow(1, 0, k), Vk));
+      EC(contract(c.st, Vk, {1, 1, 1}, Tperm, {1, 1, 3}, Operm, {1, 1, 3}));
+      done = true;
+    }
+  }
+  if (!done) {
+    Tn Vh;
+    EC(eigh(c, G, &theta, &Vh));
+    thetaStride = a;
+    Tn Vk = c.ar.alloc(dtype, {(long long)B, (long long)k, (long long)a});
+    ARENA_OK(c);
+    EC(copy_view(c.st, Vh.narrow(1, 0, k), Vk));
+    EC(contract(c.st, Vk, {1, 1, 1}, Tperm, {1, 1, 3}, Operm, {1, 1, 3}, true, false));
+  }
+  if (disc_out) {
+    discarded_kernel<<<(B + 127) / 128, 128, 0, c.st>>>(B, a, k, (const double2*)G.p, theta, thetaStride, disc_out);
+    EC(check_launch("discarded_kernel"));
+  }
+  return 0;
+}
+
+// Two-qubit gate absorption + split (Circuit.py:74-136). G [Bg,2,2,2,2,K] in (lo, hi) order, same dtype as the state.
+// The kept rank is data dependent: alloc(which, count, user) is called once the rank is known and must return device
+// memory for count complex elements (which = 0: T_lo' [B,l,2,a0,k]; 1: T_hi' [B,k,2,K*a1,r]). SYNC (rank read-back).
+extern "C" int mpdo_split_2q(int dtype, int npass, int B, int l, int a0, int m, const void* Tlo, int a1, int r,
+                             const void* Thi, int Bg, int K, const void* G, double max_err, mpdo_alloc_fn alloc,
+                             void* user, int* k_out, void* stream) {
+  Ctx c((cudaStream_t)stream, dtype, npass);
+  const long long Bn = B;
+  Tn TLO = Tn::contig((void*)Tlo, dtype, {Bn, l, 2, a0, m});
+  Tn THI = Tn::contig((void*)Thi, dtype, {Bn, m, 2, a1, r});
+  Tn Gv = Tn::contig((void*)G, dtype, {Bg, 2, 2, 2, 2, K});
+
+  // left factor: rows (l,a0), cols (s0,m)
+  Tn Xlo = TLO.permute({0, 1, 3, 2, 4});  // [B,l,a0,2,m]
+  Tn Alo, Xs_lo, Rp;
+  bool orthLo = (long long)l * a0 > 2LL * m;
+  long long x;
+  if (orthLo) {
+    EC(orth_cols(c, Xlo, {1, 2, 2}, &Alo, &Xs_lo, &Rp));
+    x = 2LL * m;
+  } else {
+    x = (long long)l * a0;
+    Rp = c.ar.alloc(MPDO_C128, {Bn, x, 2LL * m});
+    ARENA_OK(c);
+    EC(copy_view(c.st, Xlo, Rp));
+  }
+  // right factor: rows (m,s1), cols (a1,r)
+  Tn Mhi, F_hi, Lh_hi;
+  bool orthHi = (long long)a1 * r > 2LL * m;
+  long long y;
+  if (orthHi) {
+    EC(orth_rows(c, THI, {1, 2, 2}, &Mhi, &F_hi, &Lh_hi));
+    y = 2LL * m;
+  } else {
+    y = (long long)a1 * r;
+  }
+  // D[b,x,s0,s1,y] = sum_m R'[x,s0,m] L'[m,s1,y]
+  Tn D = c.ar.alloc(MPDO_C128, {Bn, x, 2, 2, y});
+  ARENA_OK(c);
+  {
+    Tn Rp5 = Rp.view({Bn, x, 2, 1, (long long)m}).expand(3, 2).permute({0, 2, 3, 1, 4});  // [b,s0,s1 | x | m]
+    Tn Dv = D.permute({0, 2, 3, 1, 4});                                                      // [b,s0,s1 | x | y]
+    if (orthHi) {
+      // L'[(m,s1),y] = conj(Lh_hi[y,(m,s1)])
+      Tn Lv = Lh_hi.view({Bn, y, (long long)m, 1, 2}).expand(3, 2).permute({0, 3, 4, 2, 1});  // [b,s0,s1 | m | y]
+      EC(contract(c.st, Rp5, {3, 1, 1}, Lv, {3, 1, 1}, Dv, {3, 1, 1}, false, true));
+    } else {
+      Tn Lv = THI.view({Bn, (long long)m, 1, 2, y}).expand(2, 2).permute({0, 2, 3, 1, 4});     // [b,s0,s1 | m | y]
+      EC(contract(c.st, Rp5, {3, 1, 1}, Lv, {3, 1, 1}, Dv, {3, 1, 1}));
+    }
+  }
+  // Cm[b,x,p0,p1,g,y] = sum_{s0,s1} G[p0,p1,s0,s1,g] D[b,x,s0,s1,y]
+  Tn Gp = c.ar.alloc(MPDO_C128, {(long long)Bg, 2, 2, (long long)K, 2, 2});
+  Tn Cm = c.ar.alloc(MPDO_C128, {Bn, x, 2, 2, (long long)K, y});
+  ARENA_OK(c);
+  EC(copy_view(c.st, Gv.permute({0, 1, 2, 5, 3, 4}), Gp));
+  {
+    Tn GpE = Gp.view({(long long)Bg, 1, 4LL * K, 4});
+    if (Bg == 1) GpE = GpE.expand(0, Bn);
+    GpE = GpE.expand(1, x);
+    EC(contract(c.st, GpE, {2, 1, 1}, D.view({Bn, x, 4, y}), {2, 1, 1}, Cm.view({Bn, x, 4LL * K, y}), {2, 1, 1}));
+  }
+  // SVD of the core as rows (x,p0) x cols (p1,g,y)
+  const long long nrow = 2 * x, ncol = 2LL * K * y;
+  Tn Cv = Cm.view({Bn, nrow, ncol});
+  const int zdt = orthHi ? MPDO_C128 : dtype;
+  Tn UL, Zc;
+  int k = 0;
+  if (nrow <= ncol) {
+    WideSvd w;
+    EC(svd_wide(c, Cv, {1, 1, 1}, &w));
+    EC(keep_rank(c, w.sv, B, w.n, w.squared, -1, max_err, false, &k));
+    EC(wide_left(c, w, k, MPDO_C128, &UL));
+    Tn right;
+    EC(wide_right(c, w, k, MPDO_C128, &right));
+    Zc = c.ar.alloc(zdt, {Bn, (long long)k, ncol});
+    ARENA_OK(c);
+    EC(contract(c.st, right, {1, 1, 1}, w.Mlast, {1, 1, 1}, Zc, {1, 1, 1}));
+  } else {
+    // tall core: decompose the column side
+    Tn Alast, Xs, R, Uh_, Wh_, su, XU;
+    double* s;
+    EC(orth_cols(c, Cv, {1, 1, 1}, &Alast, &Xs, &R));
+    EC(decompose(c, R, true, &s, &Wh_, &Uh_));  // R = Uh_^h diag(s) Wh_
+    EC(keep_rank(c, s, B, (int)ncol, false, -1, max_err, false, &k));
+    EC(rowscale(c, Uh_, s, (int)ncol, k, 0.5, 0.0, 0, MPDO_C128, &su));
+    XU = c.ar.alloc(MPDO_C128, {Bn, (long long)k, ncol});
+    UL = c.ar.alloc(MPDO_C128, {Bn, (long long)k, nrow});
+    ARENA_OK(c);
+    EC(contract(c.st, su, {1, 1, 1}, Xs, {1, 1, 1}, XU, {1, 1, 1}));
+    EC(contract(c.st, XU, {1, 1, 1}, transposed(Alast), {1, 1, 1}, UL, {1, 1, 1}, false, true));
+    EC(rowscale(c, Wh_, s, (int)ncol, k, 0.5, 0.0, 0, zdt, &Zc));
+  }
+  *k_out = k;
+  void* plo = alloc(0, (int64_t)Bn * l * 2 * a0 * k, user);
+  void* phi = alloc(1, (int64_t)Bn * k * 2 * K * a1 * r, user);
+  if (!plo || !phi) return fail(MPDO_EINVAL, "mpdo_split_2q: output allocation failed");
+  Tn Tlo_n = Tn::contig(plo, dtype, {Bn, l, 2, a0, (long long)k});
+  Tn Thi_n = Tn::contig(phi, dtype, {Bn, (long long)k, 2, (long long)K * a1, r});
+
+  // Tlo'[b,l,p0,a0,j] = sum_x Q'[(l,a0),x] conj(UL[j,(x,p0)])
+  Tn ULv = UL.view({Bn, (long long)k, x, 2});
+  if (orthLo) {
+    // W[b,c,(p0,j)] = sum_x conj(Xs_lo[x,c]) conj(UL[j,x,p0]);   Tlo' = Alo . W
+    Tn W = c.ar.alloc(dtype, {Bn, 2LL * m, 2, (long long)k});
+    ARENA_OK(c);
+    EC(contract(c.st, transposed(Xs_lo), {1, 1, 1}, ULv.permute({0, 2, 3, 1}), {1, 1, 2}, W.view({Bn, 2LL * m, 2LL * k}),
+                {1, 1, 1}, true, true));
+    EC(contract(c.st, Alo, {1, 2, 2}, W.view({Bn, 2, (long long)m, 2, (long long)k}), {1, 2, 2},
+                Tlo_n.permute({0, 1, 3, 2, 4}), {1, 2, 2}));
+  } else {
+    // Tlo'[b,l,p0,a0,j] = conj(UL[j,(l,a0),p0])
+    Tn src = UL.view({Bn, (long long)k, (long long)l, (long long)a0, 2}).permute({0, 2, 4, 3, 1});
+    EC(copy_view(c.st, src, Tlo_n, true));
+  }
+  // Thi'[b,j,p1,(g,a1),r] = sum_y Zc[j,p1,g,y] Qt'[y,(a1,r)]
+  if (orthHi) {
+    Tn ZF = c.ar.alloc(dtype, {Bn, (long long)k * 2 * K, 2LL * m});
+    ARENA_OK(c);
+    EC(contract(c.st, Zc.view({Bn, (long long)k * 2 * K, y}), {1, 1, 1}, F_hi, {1, 1, 1}, ZF, {1, 1, 1}));
+    EC(contract(c.st, ZF.view({Bn, (long long)k * 2 * K, (long long)m, 2}), {1, 1, 2}, Mhi, {1, 2, 2},
+                Thi_n.view({Bn, (long long)k * 2 * K, (long long)a1, (long long)r}), {1, 1, 2}));
+  } else {
+    EC(copy_view(c.st, Zc, Thi_n.view({Bn, (long long)k, ncol})));
+  }
+  return 0;
+}
