@@ -27,5 +27,10 @@ def engine_for(dtype):
     p = get_prims()
     key = (id(p), dtype)
     if key not in _ENGINES:
-        _ENGINES[key] = Engine(p, dtype)
+        import os
+        if getattr(p, 'name', '') == 'cuda' and os.environ.get('MPDO_ENGINE', 'native') != 'py':
+            from .native import NativeEngine          # one C call per step (csrc/engine.cu)
+            _ENGINES[key] = NativeEngine(p, dtype)
+        else:
+            _ENGINES[key] = Engine(p, dtype)          # the same sequences over the Python primitive wrappers
     return _ENGINES[key]

@@ -80,7 +80,8 @@ class NativeEngine(Engine):
         cb = ALLOC_FN(alloc)
         k = C.c_int(0)
         _lib.check(self.lib.mpdo_split_2q(self.dt, self.npass, Bn, l, a0, m, _p(Tlo), a1, r, _p(Thi), Bg, K, _p(G),
-                                          -1.0 if max_err is None else float(max_err), cb, None, C.byref(k),
+                                          -1.0 if max_err is None else float(max_err), C.cast(cb, C.c_void_p), None,
+                                          C.byref(k),
                                           _stream()), 'mpdo_split_2q')
         kk = k.value
         self.stats['last_rank'] = kk
