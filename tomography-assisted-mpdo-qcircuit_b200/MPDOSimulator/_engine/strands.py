@@ -8,6 +8,7 @@ threads, each on its own CUDA stream: the kernels of different brick pairs overl
 host-side waits (rank read-backs) overlap too. The main stream waits for every side stream afterwards, so
 callers see ordinary stream-ordered semantics.
 """
+import os
 import threading
 from concurrent.futures import ThreadPoolExecutor
 
@@ -39,6 +40,8 @@ def run_strands(tasks, device, enabled=True):
     """tasks: list of zero-argument callables, mutually independent. Runs them concurrently on side streams when
     it pays off (CUDA device, more than one task), else in order on the current stream."""
     dev = torch.device(device)
+    if os.environ.get('MPDO_STRANDS', '1') == '0':   # debugging knob: everything on the caller's stream
+        enabled = False
     if not enabled or len(tasks) < 2 or dev.type != 'cuda':
         for t in tasks:
             t()

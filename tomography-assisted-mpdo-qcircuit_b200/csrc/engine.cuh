@@ -1,6 +1,8 @@
 // Host-side building blocks of the native update-path engine (engine.cu): strided tensor views over device
 // memory, a stream-ordered scratch arena, and typed wrappers over the kernels' C entry points.
 #pragma once
+#include <string.h>
+
 #include <initializer_list>
 #include <vector>
 
@@ -81,14 +83,39 @@ struct Arena {  // scratch buffers freed (stream-ordered) when the step returns
   cudaStream_t st;
   std::vector<void*> bufs;
   int err = 0;
-  explicit Arena(cudaStream_t s) : st(s) {}
+  cudaMemPool_t pool = nullptr;
+  explicit Arena(cudaStream_t s) : st(s) {
+    // One private pool per host thread. Strands run on different streams from different threads; with the shared
+    // default pool a buffer freed on one stream and reused on another makes the second stream wait for the first
+    // (the allocator orders the reuse after the free), which serialises the strands. The release threshold keeps
+    // freed scratch cached instead of handing it back to the OS at every synchronisation.
+    static thread_local cudaMemPool_t tpool = nullptr;
+    if (!tpool) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaMemPoolProps props;
+      memset(&props, 0, sizeof(props));
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      if (cudaMemPoolCreate(&tpool, &props) == cudaSuccess) {
+        unsigned long long keep = ~0ULL;
+        cudaMemPoolSetAttribute(tpool, cudaMemPoolAttrReleaseThreshold, &keep);
+      } else {
+        tpool = nullptr;
+        cudaGetLastError();
+      }
+    }
+    pool = tpool;
+  }
   ~Arena() {
     for (void* b : bufs) cudaFreeAsync(b, st);
   }
   void* raw(size_t bytes) {
     void* ptr = nullptr;
     if (bytes == 0) bytes = 16;
-    cudaError_t e = cudaMallocAsync(&ptr, bytes, st);
+    cudaError_t e = pool ? cudaMallocFromPoolAsync(&ptr, bytes, pool, st) : cudaMallocAsync(&ptr, bytes, st);
     if (e != cudaSuccess) {
       snprintf(g_err, sizeof(g_err), "cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e));
       err = (int)e;

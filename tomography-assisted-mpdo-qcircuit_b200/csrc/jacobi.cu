@@ -37,37 +37,48 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// Rotate rows x, y (shared memory) so that their first m entries become orthogonal. Returns 1 if a
-// rotation was applied.
-__device__ __forceinline__ int rotate_pair(double2* x, double2* y, int m, int mt, double tol, double floor2,
-                                           int lane) {
+// Rotate rows x, y (shared memory) so that their first m entries become orthogonal; G lanes cooperate on one
+// pair (32/G pairs per warp). The kernel is instruction-issue bound (ncu: ~2 IPC, half of the issue slots busy, 6
+// warps per scheduler each spending ~440 instructions per rotation, most of them reduction / scalar / index
+// overhead rather than row arithmetic), so short rows share that overhead between several pairs of one warp.
+// Every lane of the warp runs the shuffles; `active` only predicates the memory traffic. Returns 1 if rotated.
+template <int G>
+__device__ __forceinline__ int rotate_pair(double2* x, double2* y, bool active, int m, int mt, double tol,
+                                           double floor2, int sub) {
   double a = 0, bq = 0, gr = 0, gi = 0;
-  for (int k = lane; k < m; k += 32) {
-    double2 u = x[k], v = y[k];
-    a = fma(u.x, u.x, fma(u.y, u.y, a));
-    bq = fma(v.x, v.x, fma(v.y, v.y, bq));
-    // g = sum x * conj(y)
-    gr = fma(u.x, v.x, fma(u.y, v.y, gr));
-    gi = fma(u.y, v.x, fma(-u.x, v.y, gi));
+  if (active) {
+    for (int k = sub; k < m; k += G) {
+      double2 u = x[k], v = y[k];
+      a = fma(u.x, u.x, fma(u.y, u.y, a));
+      bq = fma(v.x, v.x, fma(v.y, v.y, bq));
+      // g = sum x * conj(y)
+      gr = fma(u.x, v.x, fma(u.y, v.y, gr));
+      gi = fma(u.y, v.x, fma(-u.x, v.y, gi));
+    }
   }
-  a = warp_sum(a);
-  bq = warp_sum(bq);
-  gr = warp_sum(gr);
-  gi = warp_sum(gi);
+#pragma unroll
+  for (int o = G / 2; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    bq += __shfl_xor_sync(0xffffffffu, bq, o);
+    gr += __shfl_xor_sync(0xffffffffu, gr, o);
+    gi += __shfl_xor_sync(0xffffffffu, gi, o);
+  }
   const double g2 = gr * gr + gi * gi;
   const double ab = a * bq;
   // rows that are both at rounding level of the matrix scale carry no information: leave them alone
-  if (!(ab > floor2) || !(g2 > tol * tol * ab)) return 0;
-  const double g = sqrt(g2);
-  const double zeta = (bq - a) / (2.0 * g);
-  const double tt = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-  const double c = rsqrt(1.0 + tt * tt);
-  const double s = c * tt;
-  // phase e^{i phi} = g / |g|
-  const double pr = gr / g, pi = gi / g;
+  if (!active || !(ab > floor2) || !(g2 > tol * tol * ab)) return 0;
+  // Rotation by the smaller angle theta with tan(2 theta) = |g| / |d|, d = (beta - alpha)/2. With h = sqrt(d^2+|g|^2):
+  // cos(theta) = (h+|d|) / sqrt(2h(h+|d|)),  sin(theta) e^{i phi} = sign(d) g / sqrt(2h(h+|d|)):
+  // two dependent slow fp64 operations (sqrt, rsqrt) instead of the textbook chain of seven.
+  const double d = 0.5 * (bq - a);
+  const double ad = fabs(d);
+  const double h = sqrt(fma(d, d, g2));
+  const double ru = rsqrt(2.0 * h * (h + ad));
+  const double c = (h + ad) * ru;
+  const double sg = d >= 0 ? ru : -ru;
   // x' = c x - s e^{i phi} y ; y' = s e^{-i phi} x + c y
-  const double sr = s * pr, si = s * pi;
-  for (int k = lane; k < mt; k += 32) {
+  const double sr = sg * gr, si = sg * gi;
+  for (int k = sub; k < mt; k += G) {
     double2 u = x[k], v = y[k];
     double2 xn, yn;
     xn.x = c * u.x - (sr * v.x - si * v.y);
@@ -80,23 +91,28 @@ __device__ __forceinline__ int rotate_pair(double2* x, double2* y, int m, int mt
   return 1;
 }
 
-// Round-robin partner tables: `np` players (even), round r in [0, np-1), pair q in [0, np/2).
+// Round-robin partner tables: `np` players (even), round r in [0, np-1), pair q in [0, np/2). Division free.
 __device__ __forceinline__ void rr_pair(int np, int r, int q, int& p0, int& p1) {
+  const int w = np - 1;
   if (q == 0) {
-    p0 = np - 1;
-    p1 = r % (np - 1);
+    p0 = w;
+    p1 = r >= w ? r - w : r;
   } else {
-    p0 = (r + q) % (np - 1);
-    p1 = (r - q + 2 * (np - 1)) % (np - 1);
+    p0 = r + q;
+    if (p0 >= w) p0 -= w;
+    p1 = r - q + w;
+    if (p1 >= w) p1 -= w;
   }
 }
 
+template <int G>
 __global__ void __launch_bounds__(1024) jacobi_kernel(JacobiArgs p, double2* __restrict__ Yall) {
   extern __shared__ double2 smem[];  // 2b rows of mt entries
-  __shared__ int s_any;
+  constexpr int PPW = 32 / G;        // pairs per warp
   const int bidx = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = p.b;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int slot = warp * PPW + lane / G, nslots = nwarps * PPW, sub = lane % G;
+  const int b = p.b, mt = p.mt;
   int* cnt = p.cnt + (long long)bidx * WORK_INTS;
   const double amax = *reinterpret_cast<const double*>(cnt + 32);
   const double floor2 = fmax(1e-290, 1e-48 * amax * amax);
@@ -113,64 +129,64 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(JacobiArgs p, double2* __r
   double2* Y = Yall + (long long)bidx * p.batchStride;
 
   // stage the 2b rows
-  for (int v = warp; v < 2 * b; v += b) {
-    int row = (v < b) ? I * b + v : J * b + (v - b);
-    double2* dst = smem + (long long)v * p.mt;
+  for (int v = warp; v < 2 * b; v += nwarps) {
+    const int row = (v < b) ? I * b + v : J * b + (v - b);
+    double2* dst = smem + v * mt;
     if (row < p.n) {
       const double2* src = Y + (long long)row * p.ld;
-      for (int k = lane; k < p.mt; k += 32) dst[k] = src[k];
+      for (int k = lane; k < mt; k += 32) dst[k] = src[k];
     }
   }
   __syncthreads();
 
   const int be = (b + 1) & ~1;  // b rounded up to even for the intra-block tournament
+  const int half = be / 2;
   const int nsweeps = p.loop ? p.maxSweeps : 1;
   for (int sw = 0; sw < nsweeps; ++sw) {
     int rot = 0;
     if (p.loop || p.round == 0) {
       // intra-block pairs of both blocks: be/2 pairs per block per step, be-1 steps
       for (int step = 0; step < be - 1; ++step) {
-        for (int w = warp; w < be; w += b) {
-          int blk = w / (be / 2), q = w % (be / 2);
+        for (int base = 0; base < be; base += nslots) {
+          const int q = base + slot;
+          const int blk = q >= half ? 1 : 0;
           int a0, a1;
-          rr_pair(be, step, q, a0, a1);
-          int r0 = (blk ? J : I) * b + a0, r1 = (blk ? J : I) * b + a1;
-          if (a0 < b && a1 < b && r0 < p.n && r1 < p.n)
-            rot |= rotate_pair(smem + (long long)(blk * b + a0) * p.mt, smem + (long long)(blk * b + a1) * p.mt, p.m,
-                               p.mt, p.tol, floor2, lane);
+          rr_pair(be, step, q - blk * half, a0, a1);
+          const int first = (blk ? J : I) * b;
+          const bool active = q < be && a0 < b && a1 < b && first + a0 < p.n && first + a1 < p.n;
+          rot |= rotate_pair<G>(smem + (blk * b + a0) * mt, smem + (blk * b + a1) * mt, active, p.m, mt, p.tol,
+                                floor2, sub);
         }
         __syncthreads();
       }
     }
-    // cross pairs: warp w pairs row w of block I with row (w+step)%b of block J
+    // cross pairs: row q of block I with row (q+step) mod b of block J
     for (int step = 0; step < b; ++step) {
-      int a0 = warp, a1 = (warp + step) % b;
-      int r0 = I * b + a0, r1 = J * b + a1;
-      if (r0 < p.n && r1 < p.n)
-        rot |= rotate_pair(smem + (long long)a0 * p.mt, smem + (long long)(b + a1) * p.mt, p.m, p.mt, p.tol, floor2, lane);
+      for (int base = 0; base < b; base += nslots) {
+        const int q = base + slot;
+        int a1 = q + step;
+        if (a1 >= b) a1 -= b;
+        const bool active = q < b && I * b + q < p.n && J * b + a1 < p.n;
+        rot |= rotate_pair<G>(smem + q * mt, smem + (b + a1) * mt, active, p.m, mt, p.tol, floor2, sub);
+      }
       __syncthreads();
     }
     if (p.loop) {
-      if (threadIdx.x == 0) s_any = 0;
-      __syncthreads();
-      if (rot && lane == 0) atomicOr(&s_any, 1);
-      __syncthreads();
-      int any = s_any;
-      __syncthreads();
+      const int any = __syncthreads_or(rot);
       if (threadIdx.x == 0) cnt[sw] = any;
       if (!any) break;
     } else {
-      if (rot && lane == 0) atomicAdd(&cnt[p.sweep], 1);
+      if (rot && sub == 0) atomicAdd(&cnt[p.sweep], 1);
     }
   }
 
   // write back
-  for (int v = warp; v < 2 * b; v += b) {
-    int row = (v < b) ? I * b + v : J * b + (v - b);
+  for (int v = warp; v < 2 * b; v += nwarps) {
+    const int row = (v < b) ? I * b + v : J * b + (v - b);
     if (row < p.n) {
       double2* dst = Y + (long long)row * p.ld;
-      const double2* src = smem + (long long)v * p.mt;
-      for (int k = lane; k < p.mt; k += 32) dst[k] = src[k];
+      const double2* src = smem + v * mt;
+      for (int k = lane; k < mt; k += 32) dst[k] = src[k];
     }
   }
 }
@@ -303,7 +319,9 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
     int dev = 0;
     MPDO_CUDA(cudaGetDevice(&dev));
     MPDO_CUDA(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024));
+    MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024));
+    MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024));
+    MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024));
   }
   const long long rowBytes = (long long)mt * sizeof(double2);
   int bmax = (int)((smemMax - 1024) / (2 * rowBytes));
@@ -338,10 +356,21 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
   a.tol = tol;
   a.cnt = work;
   const size_t smem = (size_t)(2 * b) * rowBytes;
-  const unsigned threads = 32u * b;
+  // lanes per row pair: short rows share a warp between several pairs (see rotate_pair)
+  const int G = mt >= 384 ? 32 : (mt >= 128 ? 16 : 8);
+  const int ppw = 32 / G;
+  const unsigned threads = 32u * (unsigned)((b + ppw - 1) / ppw);
+  auto launch = [&](dim3 grid) {
+    if (G == 8)
+      jacobi_kernel<8><<<grid, threads, smem, st>>>(a, (double2*)Y);
+    else if (G == 16)
+      jacobi_kernel<16><<<grid, threads, smem, st>>>(a, (double2*)Y);
+    else
+      jacobi_kernel<32><<<grid, threads, smem, st>>>(a, (double2*)Y);
+  };
   if (nbp == 2) {
     a.loop = 1;
-    jacobi_kernel<<<dim3(1, batch), threads, smem, st>>>(a, (double2*)Y);
+    launch(dim3(1, batch));
     return check_launch("jacobi_kernel(loop)");
   }
   a.loop = 0;
@@ -349,7 +378,7 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
     a.sweep = sw;
     for (int r = 0; r < nbp - 1; ++r) {
       a.round = r;
-      jacobi_kernel<<<dim3(nbp / 2, batch), threads, smem, st>>>(a, (double2*)Y);
+      launch(dim3(nbp / 2, batch));
       int rc = check_launch("jacobi_kernel");
       if (rc) return rc;
     }
