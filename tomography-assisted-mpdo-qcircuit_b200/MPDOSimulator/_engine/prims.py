@@ -137,8 +137,8 @@ class CudaPrims:
         d.b_jfast = int(inner(lbj) <= inner(lbk))
         tiles = ((M + 63) // 64) * ((N + 63) // 64) * batch
         ksplit = 1
-        if K >= 1024 and tiles < 2 * self.sm_count:
-            ksplit = max(1, min((K + 255) // 256, (4 * self.sm_count) // max(tiles, 1)))
+        if K >= 256 and tiles < self.sm_count and Cv.is_contiguous() and beta in (0.0, 1.0):
+            ksplit = max(1, min((K + 63) // 64, (2 * self.sm_count) // max(tiles, 1)))
         d.ksplit = ksplit
         d.alpha, d.beta = float(alpha), float(beta)
         return d, ksplit

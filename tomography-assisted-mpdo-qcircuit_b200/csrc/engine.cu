@@ -115,8 +115,10 @@ int contract(cudaStream_t st, const Tn& A, Roles ra, const Tn& B, Roles rb, cons
   const long long tiles = ((M + 63) / 64) * ((N + 63) / 64) * batch;
   int ksplit = 1;
   const int sms = sm_count();
-  if (K >= 1024 && tiles < 2 * sms && C.contiguous() && (beta == 0.0 || beta == 1.0))
-    ksplit = (int)std::max(1LL, std::min((K + 255) / 256, (4LL * sms) / std::max(tiles, 1LL)));
+  // Gram matrices of the sweeps are one or two output tiles with a long K: a single CTA walking K alone is pure
+  // latency (measured 90 us for 48x48x384), so K is spread over CTAs as soon as the grid is small.
+  if (K >= 256 && tiles < sms && C.contiguous() && (beta == 0.0 || beta == 1.0))
+    ksplit = (int)std::max(1LL, std::min((K + 63) / 64, (2LL * sms) / std::max(tiles, 1LL)));
   d.ksplit = ksplit;
   d.alpha = alpha;
   d.beta = beta;

@@ -43,10 +43,12 @@ __device__ __forceinline__ double warp_sum(double v) {
 // overhead rather than row arithmetic), so short rows share that overhead between several pairs of one warp.
 // Every lane of the warp runs the shuffles; `active` only predicates the memory traffic. Returns 1 if rotated.
 template <int G>
-__device__ __forceinline__ int rotate_pair(double2* x, double2* y, bool active, int m, int mt, double tol,
+__device__ __forceinline__ int rotate_pair(double2* __restrict__ x, double2* __restrict__ y, bool active, int m,
+                                           int mt, double tol,
                                            double floor2, int sub) {
   double a = 0, bq = 0, gr = 0, gi = 0;
   if (active) {
+#pragma unroll 4
     for (int k = sub; k < m; k += G) {
       double2 u = x[k], v = y[k];
       a = fma(u.x, u.x, fma(u.y, u.y, a));
@@ -78,6 +80,7 @@ __device__ __forceinline__ int rotate_pair(double2* x, double2* y, bool active, 
   const double sg = d >= 0 ? ru : -ru;
   // x' = c x - s e^{i phi} y ; y' = s e^{-i phi} x + c y
   const double sr = sg * gr, si = sg * gi;
+#pragma unroll 4
   for (int k = sub; k < mt; k += G) {
     double2 u = x[k], v = y[k];
     double2 xn, yn;
@@ -357,7 +360,8 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
   a.cnt = work;
   const size_t smem = (size_t)(2 * b) * rowBytes;
   // lanes per row pair: short rows share a warp between several pairs (see rotate_pair)
-  const int G = mt >= 384 ? 32 : (mt >= 128 ? 16 : 8);
+  int G = mt >= 384 ? 32 : 16;   // (8 / 16 / 32 measured on n = 24, 48, 96: 16 is best or equal up to mt = 192)
+  if (const char* e = getenv("MPDO_JACOBI_G")) G = atoi(e) == 8 ? 8 : (atoi(e) == 16 ? 16 : 32);   // tuning knob
   const int ppw = 32 / G;
   const unsigned threads = 32u * (unsigned)((b + ppw - 1) / ppw);
   auto launch = [&](dim3 grid) {
