@@ -167,43 +167,6 @@ def reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------
-class TimedPrims:
-    """Wraps the device primitives to time the dominant kernel class (large contractions) with CUDA events on
-    the launching stream, inside the timed region."""
-
-    def __init__(self, prims, min_flops=2e9):
-        self.p, self.min_flops, self.records, self.enabled = prims, min_flops, [], False
-
-    def __getattr__(self, name):
-        return getattr(self.p, name)
-
-    def contract(self, A, ra, B, rb, Cv, rc, **kw):
-        if not self.enabled:
-            return self.p.contract(A, ra, B, rb, Cv, rc, **kw)
-        nb, ni, nk = ra
-        M = math.prod(A.shape[nb:nb + ni])
-        K = math.prod(A.shape[nb + ni:])
-        N = math.prod(B.shape[rb[0] + rb[1]:])
-        batch = math.prod(A.shape[:nb])
-        flops = 8.0 * M * N * K * batch
-        if flops < self.min_flops:
-            return self.p.contract(A, ra, B, rb, Cv, rc, **kw)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        out = self.p.contract(A, ra, B, rb, Cv, rc, **kw)
-        e1.record()
-        csize = lambda t: 8 if t.dtype == torch.complex64 else 16
-        byts = batch * (M * K * csize(A) + K * N * csize(B) + M * N * csize(Cv))
-        fp32 = A.dtype == B.dtype == Cv.dtype == torch.complex64 and not kw.get('acc64')
-        self.records.append((e0, e1, flops, byts, fp32, (M, N, K, batch)))
-        return out
-
-    def summary(self):
-        torch.cuda.synchronize()
-        rows = [(e0.elapsed_time(e1) * 1e-3, fl, by, fp32, shp) for e0, e1, fl, by, fp32, shp in self.records]
-        return rows
-
-
 def b200_arm(args):
     import torch.distributed as dist
     rank = int(os.environ.get('RANK', '0'))
@@ -217,9 +180,7 @@ def b200_arm(args):
     import MPDOSimulator as Simulator
     from MPDOSimulator import _engine
     base = _engine.get_prims()
-    timed = TimedPrims(base)
-    _engine._PRIMS = timed
-    _engine._ENGINES.clear()
+    lib = base.lib
 
     n, K, W = N_QUBITS, args.steps, args.warmup
     assert W >= 3, 'timing rules: at least 3 warm-up steps'
@@ -261,7 +222,7 @@ def b200_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    timed.enabled = True
+    lib.mpdo_timing_enable(1)   # CUDA events around every contraction / Jacobi launch, on the launching stream
     launches0 = base.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -278,11 +239,20 @@ def b200_arm(args):
         dist.all_gather_into_tensor(gathered, readout)
     ev1.record()
     barrier()
-    timed.enabled = False
     launches = base.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     secs = ev0.elapsed_time(ev1) * 1e-3
-    kern_rows = timed.summary()
+    def timing(cls, min_flops=0.0):
+        import ctypes as C
+        sec, fl, by, mxs, mxf = (C.c_double() for _ in range(5))
+        n = C.c_int64()
+        lib.mpdo_timing_summary(cls, float(min_flops), C.byref(sec), C.byref(fl), C.byref(by), C.byref(n),
+                                C.byref(mxs), C.byref(mxf))
+        return {'seconds': sec.value, 'flops': fl.value, 'bytes': by.value, 'launches': n.value,
+                'largest_seconds': mxs.value, 'largest_flops': mxf.value}
+
+    t_contract, t_big, t_jacobi = timing(0), timing(0, 2e9), timing(1)
+    lib.mpdo_timing_enable(0)
     bond_dims = [int(s.data.shape[4]) for s in state[:-1]]
 
     # ---- e2e: host buffers in, host buffers out, every step -------------------------------------------
@@ -342,19 +312,31 @@ def b200_arm(args):
             peaks = json.load(open(pk))
         peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)
         peak_src = 'measured (MEASURED_PEAKS.json bf16_tflops_sustained)' if peaks else 'fallback 1.4 PFLOP/s'
-        tot_t = sum(r[0] for r in kern_rows) or 1e-30
-        tot_f = sum(r[1] for r in kern_rows)
-        big = max(kern_rows, key=lambda r: r[1]) if kern_rows else None
+        ct, cf = max(t_contract['seconds'], 1e-30), t_contract['flops']
         roof = {
-            'bound': 'tensor', 'kernel': 'contract_kernel (batched complex contraction, FP32 FFMA / FP64 DFMA SIMT tiles)',
-            'achieved': tot_f / tot_t / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': tot_f / tot_t / 1e12 / peak_tf,
+            'bound': 'tensor',
+            'kernel': 'contract_kernel (batched complex contraction, FP32 FFMA / FP64 DFMA SIMT tiles), all launches',
+            'achieved': cf / ct / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': cf / ct / 1e12 / peak_tf,
             'traffic': None, 'peak_source': peak_src,
-            'launches_timed': len(kern_rows), 'kernel_seconds': tot_t, 'share_of_step': tot_t / secs,
-            'largest_launch': None if big is None else {'M_N_K_batch': big[4], 'ms': big[0] * 1e3,
-                                                        'TFLOP/s': big[1] / big[0] / 1e12, 'fp32': big[3]},
-            'note': 'algorithmic flops = 8*M*N*K per complex contraction (SURVEY 8d); launches >= 2 GFLOP timed with '
-                    'CUDA events on the launching stream inside the timed region; the denominator is the dense bf16 '
-                    'tensor peak although the kernel must deliver fp32/fp64-accurate complex arithmetic',
+            'launches_timed': t_contract['launches'], 'kernel_seconds': ct, 'share_of_step_device_time': None,
+            'algorithmic_GB_per_s': t_contract['bytes'] / ct / 1e9,
+            'launches_over_2GFLOP': {'n': t_big['launches'],
+                                     'TFLOP/s': t_big['flops'] / max(t_big['seconds'], 1e-30) / 1e12},
+            'largest_launch': {'GFLOP': t_contract['largest_flops'] / 1e9, 'ms': t_contract['largest_seconds'] * 1e3,
+                               'TFLOP/s': t_contract['largest_flops'] / max(t_contract['largest_seconds'], 1e-30) / 1e12},
+            'note': 'algorithmic flops = 8*M*N*K per complex contraction (SURVEY 8d), every launch timed with CUDA '
+                    'events on its own stream inside the timed region; the denominator is the dense bf16 tensor peak '
+                    'although the kernel must deliver fp32/fp64-accurate complex arithmetic on small cores. The '
+                    'dominant kernel of this workload by device time is the Jacobi kernel (see dominant_kernel).',
+        }
+        jt = max(t_jacobi['seconds'], 1e-30)
+        roof['share_of_step_device_time'] = ct / (ct + jt)
+        dominant = {
+            'kernel': 'jacobi_kernel (one-sided Jacobi on fp64 rows in shared memory)',
+            'launches': t_jacobi['launches'], 'kernel_seconds': jt, 'avg_launch_us': 1e6 * jt / max(t_jacobi['launches'], 1),
+            'share_of_timed_device_seconds': jt / (ct + jt),
+            'bound': 'instruction issue / shared-memory latency on 1-16 SMs per decomposition (ncu: profiles/)',
+            'note': 'kernel seconds are summed over concurrent streams, so they can exceed the wall time of the step',
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -373,7 +355,8 @@ def b200_arm(args):
                        'bond_dims_after_timed_region': bond_dims},
             'e2e': {'value': tot_e2e_updates / e2e_secs, 'unit': UNIT, 'h2d_bytes_per_step': h2d // K,
                     'd2h_bytes_per_step': d2h // K, 'ms_per_step': 1e3 * e2e_secs / K},
-            'gpu_launches': int(tot_launches), 'clocks': clocks, 'roofline': roof, 'cpu_baseline': cpu,
+            'gpu_launches': int(tot_launches), 'clocks': clocks, 'roofline': roof, 'dominant_kernel': dominant,
+            'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

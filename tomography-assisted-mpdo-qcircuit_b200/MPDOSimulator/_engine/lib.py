@@ -51,6 +51,9 @@ SYMBOLS = {
     'mpdo_split_2q': (C.c_int, [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                                C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     'mpdo_cast': (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mpdo_timing_enable': (C.c_int, [C.c_int]),
+    'mpdo_timing_summary': (C.c_int, [C.c_int, C.c_double] + [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_int64)] +
+                            [C.POINTER(C.c_double)] * 2),
     'mpdo_version': (C.c_int, []),
     'mpdo_last_error': (C.c_char_p, []),
     'mpdo_device_info': (C.c_int, [C.POINTER(C.c_int)] * 4),

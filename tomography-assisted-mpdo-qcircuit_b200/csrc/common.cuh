@@ -71,4 +71,20 @@ __device__ __forceinline__ long long map_idx(const mpdo_idxmap& m, int i) {
   return (long long)i0 * m.s0 + (long long)i1 * m.s1 + (long long)i2 * m.s2;
 }
 
+// ---- optional per-launch timing (bench.py's roofline leg): CUDA events recorded on the launching stream ----------
+extern std::atomic<int> g_timing;
+void timing_begin(int cls, double flops, double bytes, cudaStream_t st, void** token);
+void timing_end(void* token, cudaStream_t st);
+
+struct TimedLaunch {  // RAII: brackets the launches issued in its scope when timing is enabled
+  void* token = nullptr;
+  cudaStream_t st;
+  TimedLaunch(int cls, double flops, double bytes, cudaStream_t s) : st(s) {
+    if (g_timing.load(std::memory_order_relaxed)) timing_begin(cls, flops, bytes, s, &token);
+  }
+  ~TimedLaunch() {
+    if (token) timing_end(token, st);
+  }
+};
+
 }  // namespace mpdo

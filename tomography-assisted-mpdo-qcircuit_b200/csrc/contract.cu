@@ -199,8 +199,14 @@ static int launch_contract(const mpdo_contract_desc& d, const void* A, const voi
   long long grid = (long long)tilesM * tilesN * ksplit * d.batch;
   if (grid <= 0) return 0;
   if (grid > 2147483647LL) return fail(MPDO_EINVAL, "mpdo_contract: grid too large");
-  contract_kernel<TA, TB, TC, R><<<(unsigned)grid, NT, 0, st>>>(d, (const TA*)A, (const TB*)B, (TC*)C, tilesM,
-                                                                  tilesN, kChunk);
+  {
+    const double mnk = (double)d.M * d.N * d.K * d.batch;
+    const double byts = (double)d.batch * ((double)d.M * d.K * sizeof(TA) + (double)d.K * d.N * sizeof(TB) +
+                                           (double)d.M * d.N * sizeof(TC));
+    TimedLaunch timed(0, 8.0 * mnk, byts, st);   // algorithmic cost of a complex contraction
+    contract_kernel<TA, TB, TC, R><<<(unsigned)grid, NT, 0, st>>>(d, (const TA*)A, (const TB*)B, (TC*)C, tilesM,
+                                                                    tilesN, kChunk);
+  }
   return check_launch("contract_kernel");
 }
 

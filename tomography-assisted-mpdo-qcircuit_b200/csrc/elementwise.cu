@@ -1,10 +1,43 @@
 // HBM-bound helpers of the MPDO update path (sm_100a): single-qubit gate / Kraus absorption,
 // row scaling of small cores, the reference's kept-rank rule, dtype casts; plus library info.
+#include <mutex>
+#include <vector>
+
 #include "common.cuh"
 
 namespace mpdo {
 
 thread_local char g_err[512] = "";
+std::atomic<int> g_timing{0};
+
+namespace {
+struct TimingRec {
+  cudaEvent_t e0, e1;
+  int cls;
+  double flops, bytes;
+};
+std::mutex g_tmutex;
+std::vector<TimingRec*> g_trecs;
+}  // namespace
+
+void timing_begin(int cls, double flops, double bytes, cudaStream_t st, void** token) {
+  TimingRec* r = new TimingRec;
+  r->cls = cls;
+  r->flops = flops;
+  r->bytes = bytes;
+  cudaEventCreate(&r->e0);
+  cudaEventCreate(&r->e1);
+  cudaEventRecord(r->e0, st);
+  *token = r;
+}
+
+void timing_end(void* token, cudaStream_t st) {
+  TimingRec* r = (TimingRec*)token;
+  cudaEventRecord(r->e1, st);
+  std::lock_guard<std::mutex> lock(g_tmutex);
+  g_trecs.push_back(r);
+}
+
 std::atomic<long long> g_launches{0};
 
 // Tout[bl, p, g, e] = sum_s G[p, s, g] * T[bl, s, e]     (e = (a, r) flattened, bl = (batch, l))
@@ -193,6 +226,48 @@ extern "C" int mpdo_cast(int dtypeIn, int dtypeOut, int64_t count, const void* i
   else
     cast_kernel<double2, double2><<<gx, 256, 0, st>>>(count, (const double2*)in, (double2*)out);
   return check_launch("cast_kernel");
+}
+
+extern "C" int mpdo_timing_enable(int on) {
+  using namespace mpdo;
+  std::lock_guard<std::mutex> lock(g_tmutex);
+  for (TimingRec* r : g_trecs) {
+    cudaEventDestroy(r->e0);
+    cudaEventDestroy(r->e1);
+    delete r;
+  }
+  g_trecs.clear();
+  g_timing.store(on ? 1 : 0);
+  return 0;
+}
+
+extern "C" int mpdo_timing_summary(int cls, double minFlops, double* seconds, double* flops, double* bytes,
+                                   int64_t* launches, double* maxFlopsSeconds, double* maxFlops) {
+  using namespace mpdo;
+  MPDO_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(g_tmutex);
+  double sec = 0, fl = 0, by = 0, bestF = -1, bestS = 0;
+  int64_t n = 0;
+  for (TimingRec* r : g_trecs) {
+    if (r->cls != cls || r->flops < minFlops) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, r->e0, r->e1) != cudaSuccess) continue;
+    sec += ms * 1e-3;
+    fl += r->flops;
+    by += r->bytes;
+    ++n;
+    if (r->flops > bestF) {
+      bestF = r->flops;
+      bestS = ms * 1e-3;
+    }
+  }
+  if (seconds) *seconds = sec;
+  if (flops) *flops = fl;
+  if (bytes) *bytes = by;
+  if (launches) *launches = n;
+  if (maxFlopsSeconds) *maxFlopsSeconds = bestS;
+  if (maxFlops) *maxFlops = bestF < 0 ? 0 : bestF;
+  return 0;
 }
 
 extern "C" int mpdo_version(void) { return 100; }
