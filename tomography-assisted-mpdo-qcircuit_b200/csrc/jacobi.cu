@@ -194,6 +194,104 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(JacobiArgs p, double2* __r
   }
 }
 
+// Device-wide barrier between the CTAs that work on one matrix (grid.x of them; the kernel is launched
+// cooperatively, so they are co-resident). `bar` only ever increases: round `phase` completes at (phase+1)*nblk.
+__device__ __forceinline__ void matrix_barrier(unsigned* bar, unsigned nblk, unsigned& phase, int* errflag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned target = (phase + 1u) * nblk;
+    unsigned spins = 0;
+    while (*((volatile unsigned*)bar) < target) {
+      __nanosleep(40);
+      if (++spins > (1u << 26)) {  // ~seconds: never expected; refuse to hang the device
+        *errflag = 1;
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  ++phase;
+}
+
+// Persistent variant for matrices that span several block pairs: one cooperative launch runs every round of every
+// sweep, the CTAs of a matrix meeting at a device-wide barrier after each round and reading the sweep's rotation
+// count to stop together. Replaces ~(nbp-1) launches plus one host synchronisation per sweep of the multi-launch
+// driver (34k launches per cfg2 layer in steady state), which is what bounded large cores.
+template <int G>
+__global__ void __launch_bounds__(1024) jacobi_persistent_kernel(JacobiArgs p, double2* __restrict__ Yall) {
+  extern __shared__ double2 smem[];
+  constexpr int PPW = 32 / G;
+  const int bidx = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int slot = warp * PPW + lane / G, nslots = nwarps * PPW, sub = lane % G;
+  const int b = p.b, mt = p.mt;
+  int* cnt = p.cnt + (long long)bidx * WORK_INTS;
+  const double amax = *reinterpret_cast<const double*>(cnt + 32);
+  const double floor2 = fmax(1e-290, 1e-48 * amax * amax);
+  unsigned* bar = reinterpret_cast<unsigned*>(cnt + 34);
+  int* errflag = cnt + 35;
+  unsigned phase = 0;
+  double2* Y = Yall + (long long)bidx * p.batchStride;
+  const int be = (b + 1) & ~1;
+  const int half = be / 2;
+
+  for (int sw = 0; sw < p.maxSweeps; ++sw) {
+    for (int round = 0; round < p.nbp - 1; ++round) {
+      int I, J;
+      rr_pair(p.nbp, round, blockIdx.x, I, J);
+      for (int v = warp; v < 2 * b; v += nwarps) {  // stage (L2 reads: other SMs wrote these rows last round)
+        const int row = (v < b) ? I * b + v : J * b + (v - b);
+        double2* dst = smem + v * mt;
+        if (row < p.n) {
+          const double2* src = Y + (long long)row * p.ld;
+          for (int k = lane; k < mt; k += 32) dst[k] = __ldcg(src + k);
+        }
+      }
+      __syncthreads();
+      int rot = 0;
+      if (round == 0) {
+        for (int step = 0; step < be - 1; ++step) {
+          for (int base = 0; base < be; base += nslots) {
+            const int q = base + slot;
+            const int blk = q >= half ? 1 : 0;
+            int a0, a1;
+            rr_pair(be, step, q - blk * half, a0, a1);
+            const int first = (blk ? J : I) * b;
+            const bool active = q < be && a0 < b && a1 < b && first + a0 < p.n && first + a1 < p.n;
+            rot |= rotate_pair<G>(smem + (blk * b + a0) * mt, smem + (blk * b + a1) * mt, active, p.m, mt, p.tol,
+                                  floor2, sub);
+          }
+          __syncthreads();
+        }
+      }
+      for (int step = 0; step < b; ++step) {
+        for (int base = 0; base < b; base += nslots) {
+          const int q = base + slot;
+          int a1 = q + step;
+          if (a1 >= b) a1 -= b;
+          const bool active = q < b && I * b + q < p.n && J * b + a1 < p.n;
+          rot |= rotate_pair<G>(smem + q * mt, smem + (b + a1) * mt, active, p.m, mt, p.tol, floor2, sub);
+        }
+        __syncthreads();
+      }
+      for (int v = warp; v < 2 * b; v += nwarps) {  // write back
+        const int row = (v < b) ? I * b + v : J * b + (v - b);
+        if (row < p.n) {
+          double2* dst = Y + (long long)row * p.ld;
+          const double2* src = smem + v * mt;
+          for (int k = lane; k < mt; k += 32) dst[k] = src[k];
+        }
+      }
+      if (rot && sub == 0) atomicAdd(&cnt[sw], 1);
+      matrix_barrier(bar, gridDim.x, phase, errflag);
+    }
+    if (*((volatile int*)&cnt[sw]) == 0 || *((volatile int*)errflag)) break;
+  }
+}
+
 // max over rows of |row[0..m)|^2, stored as a double after the 32 sweep counters of each batch entry
 __global__ void __launch_bounds__(256) row_norm_max_kernel(int n, int m, int ld, long long batchStride,
                                                            const double2* __restrict__ Yall, int* __restrict__ work) {
@@ -379,6 +477,33 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
     return check_launch("jacobi_kernel(loop)");
   }
   a.loop = 0;
+  // Persistent path: every CTA of the grid must be resident at once (device-wide barrier inside the kernel).
+  {
+    static int coop = -1, sms = 0;
+    if (coop < 0) {
+      int dev = 0;
+      MPDO_CUDA(cudaGetDevice(&dev));
+      MPDO_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+      MPDO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      MPDO_CUDA(cudaFuncSetAttribute(jacobi_persistent_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     smemMax - 1024));
+      MPDO_CUDA(cudaFuncSetAttribute(jacobi_persistent_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     smemMax - 1024));
+      if (getenv("MPDO_JACOBI_MULTILAUNCH")) coop = 0;   // debugging knob
+    }
+    const long long ctas = (long long)(nbp / 2) * batch;
+    if (coop && ctas <= sms) {   // one CTA per SM (the row staging area takes most of the shared memory)
+      TimedLaunch timed(1, 0.0, 0.0, st);
+      void* args[] = {(void*)&a, (void*)&Y};
+      const void* fn = G == 32 ? (const void*)jacobi_persistent_kernel<32> : (const void*)jacobi_persistent_kernel<16>;
+      cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(nbp / 2, batch), dim3(threads), args, smem, st);
+      if (e == cudaSuccess) {
+        ++g_launches;
+        return 0;
+      }
+      cudaGetLastError();   // e.g. cudaErrorCooperativeLaunchTooLarge: fall through to the multi-launch driver
+    }
+  }
   for (int sw = 0; sw < maxSweeps; ++sw) {
     a.sweep = sw;
     for (int r = 0; r < nbp - 1; ++r) {
