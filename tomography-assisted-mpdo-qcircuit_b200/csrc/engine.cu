@@ -218,7 +218,11 @@ struct Ctx {
   bool f32;
   int npass;   // 1: Gram-eig once (complex64), 2: twice + Jacobi SVD of the core (complex128)
   double null_tol = 1e-14, floor_tol = 1e-13, jtol = 1e-15;
-  Ctx(cudaStream_t s, int dtype, int np) : st(s), ar(s), dt(dtype), f32(dtype == MPDO_C64), npass(np) {}
+  Ctx(cudaStream_t s, int dtype, int np) : st(s), ar(s), dt(dtype), f32(dtype == MPDO_C64), npass(np) {
+    // complex64 states are stored in fp32: rows orthogonal to 1e-10 relative are far below what the state can
+    // represent, and Jacobi converges quadratically, so this saves the last sweep or two of every decomposition
+    if (f32) jtol = 1e-10;
+  }
 };
 
 #define EC(call)            \

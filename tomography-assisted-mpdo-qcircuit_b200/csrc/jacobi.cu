@@ -408,6 +408,8 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   MPDO_CUDA(cudaMemsetAsync(work, 0, sizeof(int32_t) * WORK_INTS * (size_t)batch, st));
   if (n == 1) return 0;
+  static const bool trace = getenv("MPDO_TRACE") != nullptr;
+  if (trace) fprintf(stderr, "[mpdo] jacobi n=%d m=%d mt=%d batch=%d\n", n, m, mt, batch);
   if (batch > 65535) return fail(MPDO_EINVAL, "mpdo_jacobi_rows: batch > 65535");
   row_norm_max_kernel<<<batch, 256, 0, st>>>(n, m, ld, batchStride, (const double2*)Y, work);
   {
