@@ -101,6 +101,33 @@ int mpdo_rows_finalize(int batch, int n, int m, int mz, int ld, int64_t batchStr
 int mpdo_decompose_rows(int batch, int n, int m, const void* L, void* Y, int32_t* work, double* s, void* Yn,
                         void* Z, int normalize, double zeroTol, double tol, int maxSweeps, void* stream);
 
+/* Eigen-decomposition of Hermitian positive-semidefinite matrices G[b] (n x n, complex128, dense):
+ *   G = Vh^h diag(lam) Vh,  lam[b,n] descending, Vh[b,n,n] rows = eigenvectors (conjugated).
+ * precondition = 1: rank-revealing pivoted Cholesky G = L L^h, then one-sided Jacobi on the rows of L^h
+ *   (Drmac-Veselic preconditioning: a handful of sweeps on rows of length n even for graded spectra). Directions
+ *   whose pivot falls below rel * max diag(G) are treated as the null space: lam = 0 and zero rows of Vh.
+ * precondition = 0: Jacobi on [G | I] (mpdo_decompose_rows); complete orthonormal basis.
+ * `scratch`: mpdo_eigh_psd_scratch_bytes(batch, n) bytes of device memory, 256-byte aligned.
+ * Replaces: the LAPACK eigen/SVD work behind torch.linalg.svd / torch.linalg.qr at decompositions.py:45,113,187
+ * for every Gram matrix of the truncation path (TNNOptimizer.py:143-215 sweeps, Tools.py gate split). */
+int64_t mpdo_eigh_psd_scratch_bytes(int batch, int n);
+int mpdo_eigh_psd(int batch, int n, const void* G, void* scratch, double* lam, void* Vh, int precondition,
+                  double rel, double tol, int maxSweeps, void* stream);
+
+/* Rank-revealing pivoted Cholesky factorisation of Hermitian PSD matrices G[b] (n x n, complex128, dense):
+ *   G = Lh^h Lh,  Lh[b,k,:] = conj(column k of L), columns in pivot order, rows >= rank[b] are zero;
+ *   Linv (optional) is the matching left inverse: Linv . Lh^h = diag(1 (rank times), 0, ...), rows >= rank zero.
+ * The factorisation stops when the largest remaining diagonal falls below rel * max diag(G).
+ * This is all an orthogonalisation needs (Cholesky-QR): for a tall X with G = X^h X,  Q = X . Linv^h is an isometry
+ * on the numerical range and X = Q . Lh; for a wide M with G = M M^h,  Qt = Linv . M and M = Lh^h . Qt.
+ * `scratch`: mpdo_chol_psd_scratch_bytes(batch, n) bytes, 256-byte aligned. rank: [batch] int32 on the device or NULL.
+ * Returns MPDO_ENOSMEM when batch * ceil(n / rows per CTA) CTAs cannot be co-resident (use mpdo_eigh_psd then).
+ * Replaces: torch.linalg.qr (LAPACK geqrf/ungqr) at decompositions.py:187 for the left-to-right sweep
+ * (TNNOptimizer.py:143-170) and for the two site factorisations of the gate split. */
+int64_t mpdo_chol_psd_scratch_bytes(int batch, int n);
+int mpdo_chol_psd(int batch, int n, const void* G, void* scratch, void* Lh, void* Linv, int32_t* rank, double rel,
+                  void* stream);
+
 /* X[b,j,c] = f(lam[b,j]) * V[b,j,c] for j < rows, c < cols, with f(x) = x^power and
  *   mode 0: f = 0 where lam[b,j] <= tol*lam[b,0]      (drop numerically null directions)
  *   mode 1: lam clamped from below at tol*lam[b,0]    (floor, for the first pass of a two-pass orthogonalisation)

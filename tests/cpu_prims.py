@@ -55,7 +55,7 @@ class CpuPrims:
         out = torch.einsum('bpsg,blsar->blpgar', Ge, T)
         return out.reshape(Bn, l, 2, K * a, r).contiguous()
 
-    def eigh_psd(self, G, tol=1e-15, sweeps=30):
+    def eigh_psd(self, G, tol=1e-15, sweeps=30, rank_revealing=False):
         self.calls += 1
         lam, V = torch.linalg.eigh(G)
         lam = lam.flip(-1).clamp_min(0.0).contiguous()

@@ -111,6 +111,73 @@ def test_eigh_psd_rank_deficient_and_degenerate(cuda_prims):
     rec = Vh.mH @ (lam.to(C128)[:, :, None] * Vh)
     assert (rec - G).abs().max() <= 1e-12 * G.abs().max()
 
+@pytest.mark.gpu
+@pytest.mark.parametrize('n,rk,Bn', [(1, 1, 2), (2, 2, 3), (24, 24, 5), (40, 7, 2), (100, 60, 3), (113, 113, 2),
+                                     (130, 90, 2), (256, 256, 1), (400, 300, 1), (512, 512, 1)])
+def test_eigh_psd_rank_revealing(cuda_prims, n, rk, Bn):
+    """Pivoted-Cholesky preconditioned route: graded spectrum, numerical rank rk < n, batch."""
+    A = rnd((Bn, n, rk), C128, 21)
+    A = A * torch.logspace(0, -5, rk, dtype=torch.float64)       # eigenvalues graded over ten decades
+    G = A @ A.mH
+    G = 0.5 * (G + G.mH)
+    lam_g, Vh_g = cuda_prims.eigh_psd(G.cuda(), rank_revealing=True)
+    lam_g, Vh_g = lam_g.cpu(), Vh_g.cpu()
+    lam_c = torch.linalg.eigvalsh(G).flip(-1).clamp_min(0.0)
+    top = lam_c.max()
+    assert (lam_g - lam_c).abs().max() <= 1e-12 * top
+    # high relative accuracy on the resolved part of the spectrum (the point of preconditioned Jacobi)
+    big = lam_c > 1e-9 * top
+    assert ((lam_g - lam_c).abs()[big] <= 1e-6 * lam_c[big]).all()
+    rec = Vh_g.mH @ (lam_g.to(C128)[:, :, None] * Vh_g)
+    assert (rec - G).abs().max() <= 1e-12 * G.abs().max()
+    # rows are orthonormal or zero
+    gram = Vh_g @ Vh_g.mH
+    d = gram.diagonal(dim1=1, dim2=2).real
+    assert (((d - 1).abs() <= 1e-10) | (d.abs() <= 1e-300)).all()
+    off = gram - torch.diag_embed(gram.diagonal(dim1=1, dim2=2))
+    assert off.abs().max() <= 1e-10
+    assert (lam_g[:, rk:] <= 1e-12 * top).all()
+
+
+@pytest.mark.gpu
+def test_eigh_psd_rank_revealing_zero_and_identity(cuda_prims):
+    G = torch.zeros((3, 16, 16), dtype=C128)
+    G[1] = torch.eye(16, dtype=C128) * 3.0
+    G[2, 5, 5] = 2.0
+    lam, Vh = cuda_prims.eigh_psd(G.cuda(), rank_revealing=True)
+    lam, Vh = lam.cpu(), Vh.cpu()
+    assert lam[0].abs().max() == 0 and Vh[0].abs().max() == 0
+    assert (lam[1] - 3.0).abs().max() <= 1e-14
+    assert abs(lam[2, 0] - 2.0) <= 1e-14 and lam[2, 1:].abs().max() == 0
+    rec = Vh.mH @ (lam.to(C128)[:, :, None] * Vh)
+    assert (rec - G).abs().max() <= 1e-13
+
+
+@pytest.mark.parametrize('n,rk,Bn', [(1, 1, 2), (3, 2, 2), (24, 24, 4), (60, 31, 3), (84, 84, 1), (85, 85, 2),
+                                     (130, 70, 2), (256, 256, 1), (512, 400, 1)])
+def test_chol_psd(cuda_prims, n, rk, Bn):
+    """Pivoted Cholesky with left inverse: the two identities every Cholesky-QR step of the engine relies on."""
+    A = rnd((Bn, n, rk), C128, 31)
+    A = A * torch.logspace(0, -4, rk, dtype=torch.float64)
+    G = A @ A.mH
+    G = 0.5 * (G + G.mH)
+    Lh, Linv, rank = cuda_prims.chol_psd(G.cuda(), rel=1e-12)
+    Lh, Linv, rank = Lh.cpu(), Linv.cpu(), rank.cpu()
+    assert (rank <= rk).all() and (rank >= min(rk, 1)).all()
+    assert (Lh.mH @ Lh - G).abs().max() <= 1e-12 * G.abs().max()
+    for b in range(Bn):
+        r = int(rank[b])
+        P = Linv[b] @ Lh[b].mH
+        want = torch.zeros(n, dtype=torch.float64)
+        want[:r] = 1.0
+        assert (P - torch.diag(want).to(C128)).abs().max() <= 1e-8
+        assert Lh[b, r:].abs().max() == 0 if r < n else True
+        assert Linv[b, r:].abs().max() == 0 if r < n else True
+        # pivot order: the diagonal of the factor decreases
+        piv = (Lh[b, :r].abs() ** 2).sum(1)
+        assert piv[0] >= piv[-1]
+
+
 
 @pytest.mark.parametrize('n,m', [(4, 4), (20, 33), (64, 64), (90, 70), (130, 130)])
 def test_svd_rows(cuda_prims, n, m):

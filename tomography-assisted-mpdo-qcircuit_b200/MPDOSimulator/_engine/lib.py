@@ -39,6 +39,12 @@ SYMBOLS = {
                                                     C.c_int, C.c_double, C.c_void_p]),
     'mpdo_decompose_rows': (C.c_int, [C.c_int] * 3 + [C.c_void_p] * 6 + [C.c_int, C.c_double, C.c_double, C.c_int,
                                                                     C.c_void_p]),
+    'mpdo_eigh_psd_scratch_bytes': (C.c_int64, [C.c_int, C.c_int]),
+    'mpdo_eigh_psd': (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double,
+                                C.c_double, C.c_int, C.c_void_p]),
+    'mpdo_chol_psd_scratch_bytes': (C.c_int64, [C.c_int, C.c_int]),
+    'mpdo_chol_psd': (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_double, C.c_void_p]),
     'mpdo_rowscale': (C.c_int, [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int,
                                                C.c_int, C.c_void_p, C.c_void_p]),
     'mpdo_rank_rule': (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,

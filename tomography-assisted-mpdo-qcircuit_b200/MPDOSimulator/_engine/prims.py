@@ -172,10 +172,38 @@ class CudaPrims:
                    'mpdo_decompose_rows')
         return s, Yn, Z
 
-    def eigh_psd(self, G, tol=1e-15, sweeps=30):
-        """Hermitian PSD G [B,n,n] (complex128) -> lam [B,n] descending, Vh [B,n,n] with G = Vh^h diag(lam) Vh."""
-        lam, _, Vh = self._decompose(G.contiguous(), False, 0, 0.0, tol, sweeps)
+    def eigh_psd(self, G, tol=1e-15, sweeps=30, rank_revealing=False, rel=1e-15):
+        """Hermitian PSD G [B,n,n] (complex128) -> lam [B,n] descending, Vh [B,n,n] with G = Vh^h diag(lam) Vh.
+        rank_revealing: pivoted-Cholesky preconditioned route (mpdo_eigh_psd); directions below rel * max diag come
+        back as lam = 0 with zero rows of Vh. Otherwise the complete basis from Jacobi on [G | I]."""
+        G = G.contiguous()
+        Bn, n, _ = G.shape
+        assert G.dtype == torch.complex128
+        dev = G.device
+        nbytes = int(self.lib.mpdo_eigh_psd_scratch_bytes(Bn, n))
+        scratch = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        lam = torch.empty((Bn, n), dtype=torch.float64, device=dev)
+        Vh = torch.empty((Bn, n, n), dtype=torch.complex128, device=dev)
+        tol = max(tol, 4.4e-16 * (n ** 0.5))
+        _lib.check(self.lib.mpdo_eigh_psd(Bn, n, self._ptr(G), self._ptr(scratch), self._ptr(lam), self._ptr(Vh),
+                                          1 if rank_revealing else 0, float(rel), float(tol), int(sweeps),
+                                          self._stream()), 'mpdo_eigh_psd')
         return lam, Vh
+
+    def chol_psd(self, G, rel=1e-14):
+        """Rank-revealing pivoted Cholesky of Hermitian PSD G [B,n,n] (complex128): (Lh, Linv, rank) with
+        G = Lh^h Lh and Linv . Lh^h = diag(1 x rank, 0) (see mpdo_chol_psd)."""
+        G = G.contiguous()
+        Bn, n, _ = G.shape
+        assert G.dtype == torch.complex128
+        dev = G.device
+        scratch = torch.empty((int(self.lib.mpdo_chol_psd_scratch_bytes(Bn, n)),), dtype=torch.uint8, device=dev)
+        Lh = torch.empty((Bn, n, n), dtype=torch.complex128, device=dev)
+        Linv = torch.empty((Bn, n, n), dtype=torch.complex128, device=dev)
+        rank = torch.empty((Bn,), dtype=torch.int32, device=dev)
+        _lib.check(self.lib.mpdo_chol_psd(Bn, n, self._ptr(G), self._ptr(scratch), self._ptr(Lh), self._ptr(Linv),
+                                          self._ptr(rank), float(rel), self._stream()), 'mpdo_chol_psd')
+        return Lh, Linv, rank
 
     def svd_rows(self, L, tol=1e-15, sweeps=30, zero_tol=1e-300):
         """L [B,n,m] (complex128) = Uh^h diag(s) Wh -> (Uh [B,n,n], s [B,n] descending, Wh [B,n,m])."""

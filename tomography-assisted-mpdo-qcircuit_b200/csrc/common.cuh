@@ -71,6 +71,34 @@ __device__ __forceinline__ long long map_idx(const mpdo_idxmap& m, int i) {
   return (long long)i0 * m.s0 + (long long)i1 * m.s1 + (long long)i2 * m.s2;
 }
 
+#ifdef __CUDACC__
+// Device-wide barrier between the CTAs that work on one matrix (grid.x of them; the kernel is launched
+// cooperatively, so they are co-resident). `bar` only ever increases: round `phase` completes at (phase+1)*nblk.
+__device__ __forceinline__ void matrix_barrier(unsigned* bar, unsigned nblk, unsigned& phase, int* errflag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned target = (phase + 1u) * nblk;
+    unsigned spins = 0;
+    while (*((volatile unsigned*)bar) < target) {
+      __nanosleep(40);
+      if (++spins > (1u << 26)) {  // ~seconds: never expected; refuse to hang the device
+        *errflag = 1;
+        break;
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  ++phase;
+}
+#endif
+
+// jacobi.cu: mpdo_jacobi_rows with an optional per-matrix count of non-zero leading rows (device memory)
+int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchStride, void* Y, double tol,
+                       int maxSweeps, int32_t* work, const int* rank, int rankStride, void* stream);
+
 // ---- optional per-launch timing (bench.py's roofline leg): CUDA events recorded on the launching stream ----------
 extern std::atomic<int> g_timing;
 void timing_begin(int cls, double flops, double bytes, cudaStream_t st, void** token);

@@ -217,12 +217,15 @@ struct Ctx {
   int dt;      // dtype of the state tensors
   bool f32;
   int npass;   // 1: Gram-eig once (complex64), 2: twice + Jacobi SVD of the core (complex128)
-  double null_tol = 1e-14, floor_tol = 1e-13, jtol = 1e-15;
+  double null_tol = 1e-14, floor_tol = 1e-13, jtol = 1e-15, chol_rel = 1e-15;
   Ctx(cudaStream_t s, int dtype, int np) : st(s), ar(s), dt(dtype), f32(dtype == MPDO_C64), npass(np) {
     // complex64 states are stored in fp32: rows orthogonal to 1e-10 relative are far below what the state can
     // represent, and Jacobi converges quadratically, so this saves the last sweep or two of every decomposition
     if (f32) jtol = 1e-10;
+    static const bool noChol = getenv("MPDO_NO_CHOLQR") != nullptr;   // debugging knob
+    use_chol = !noChol;
   }
+  bool use_chol = true;
 };
 
 #define EC(call)            \
@@ -250,8 +253,30 @@ static int decompose(Ctx& c, const Tn& L, bool wantRows, double** s, Tn* Yn, Tn*
 
 // G = Vh^h diag(lam) Vh (Hermitian PSD, complex128 contiguous [B,n,n])
 static int eigh(Ctx& c, const Tn& G, double** lam, Tn* Vh) {
+  if (c.npass == 1) {
+    // complex64 states: null directions are zeroed downstream anyway (null_tol), so the rank-revealing
+    // preconditioned route applies. The two-pass complex128 path needs the complete basis of its first pass.
+    const int B = (int)G.sh[0], n = (int)G.sh[1];
+    void* scratch = c.ar.raw((size_t)mpdo_eigh_psd_scratch_bytes(B, n));
+    *lam = c.ar.reals((long long)B * n);
+    *Vh = c.ar.alloc(MPDO_C128, {(long long)B, (long long)n, (long long)n});
+    ARENA_OK(c);
+    return mpdo_eigh_psd(B, n, G.p, scratch, *lam, Vh->p, 1, c.chol_rel, std::max(c.jtol, 4.4e-16 * sqrt((double)n)),
+                         30, c.st);
+  }
   Tn none;
   return decompose(c, G, false, lam, &none, Vh);
+}
+
+// Pivoted Cholesky G = Lh^h Lh with the left inverse Linv (mpdo_chol_psd). MPDO_ENOSMEM: shape not schedulable,
+// the caller uses the eigen route instead.
+static int chol(Ctx& c, const Tn& G, Tn* Lh, Tn* Linv) {
+  const long long B = G.sh[0], n = G.sh[1];
+  void* scratch = c.ar.raw((size_t)mpdo_chol_psd_scratch_bytes((int)B, (int)n));
+  *Lh = c.ar.alloc(MPDO_C128, {B, n, n});
+  *Linv = c.ar.alloc(MPDO_C128, {B, n, n});
+  ARENA_OK(c);
+  return mpdo_chol_psd((int)B, (int)n, G.p, scratch, Lh->p, Linv->p, nullptr, c.null_tol, c.st);
 }
 
 static int rowscale(Ctx& c, const Tn& V, const double* lam, int lamStride, int rows, double power, double tol, int mode,
@@ -339,6 +364,14 @@ static int orth_cols(Ctx& c, const Tn& X, Roles r, Tn* Alast, Tn* Xs, Tn* R) {
   Tn G, Vh;
   double* lam;
   EC(gram_cols(c, X, r, &G));
+  if (c.npass == 1 && c.use_chol) {   // Cholesky-QR: Q = X . Linv^h, R = Lh (no eigen-decomposition needed)
+    const int rc = chol(c, G, R, Xs);
+    if (rc == 0) {
+      *Alast = X;
+      return 0;
+    }
+    if (rc != MPDO_ENOSMEM) return rc;
+  }
   EC(eigh(c, G, &lam, &Vh));
   const int n = (int)G.sh[1];
   if (c.npass == 1) {
@@ -371,6 +404,14 @@ static int orth_rows(Ctx& c, const Tn& M, Roles r, Tn* Mlast, Tn* F, Tn* Lh, dou
   Tn G, Uh;
   double* lam;
   EC(gram_rows(c, M, r, &G));
+  if (c.npass == 1 && c.use_chol && !lam_out && !Uh_out) {   // Qt = Linv . M, M = Lh^h . Qt
+    const int rc = chol(c, G, Lh, F);
+    if (rc == 0) {
+      *Mlast = M;
+      return 0;
+    }
+    if (rc != MPDO_ENOSMEM) return rc;
+  }
   EC(eigh(c, G, &lam, &Uh));
   const int n = (int)G.sh[1];
   if (lam_out) *lam_out = lam;

@@ -27,6 +27,8 @@ struct JacobiArgs {
   int loop;    // 1: whole matrix in this CTA, loop sweeps in-kernel
   double tol;
   int* cnt;    // [batch][WORK_INTS]: 32 per-sweep rotation counters, then one double = max row norm^2
+  const int* rank;   // optional [batch * rankStride]: only the first rank[b] rows of matrix b are non-zero
+  int rankStride;
 };
 
 constexpr int WORK_INTS = 48;
@@ -130,12 +132,13 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(JacobiArgs p, double2* __r
     rr_pair(p.nbp, p.round, blockIdx.x, I, J);
   }
   double2* Y = Yall + (long long)bidx * p.batchStride;
+  const int nrows = p.rank ? min(p.n, p.rank[(long long)bidx * p.rankStride]) : p.n;
 
   // stage the 2b rows
   for (int v = warp; v < 2 * b; v += nwarps) {
     const int row = (v < b) ? I * b + v : J * b + (v - b);
     double2* dst = smem + v * mt;
-    if (row < p.n) {
+    if (row < nrows) {
       const double2* src = Y + (long long)row * p.ld;
       for (int k = lane; k < mt; k += 32) dst[k] = src[k];
     }
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(JacobiArgs p, double2* __r
           int a0, a1;
           rr_pair(be, step, q - blk * half, a0, a1);
           const int first = (blk ? J : I) * b;
-          const bool active = q < be && a0 < b && a1 < b && first + a0 < p.n && first + a1 < p.n;
+          const bool active = q < be && a0 < b && a1 < b && first + a0 < nrows && first + a1 < nrows;
           rot |= rotate_pair<G>(smem + (blk * b + a0) * mt, smem + (blk * b + a1) * mt, active, p.m, mt, p.tol,
                                 floor2, sub);
         }
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(JacobiArgs p, double2* __r
         const int q = base + slot;
         int a1 = q + step;
         if (a1 >= b) a1 -= b;
-        const bool active = q < b && I * b + q < p.n && J * b + a1 < p.n;
+        const bool active = q < b && I * b + q < nrows && J * b + a1 < nrows;
         rot |= rotate_pair<G>(smem + q * mt, smem + (b + a1) * mt, active, p.m, mt, p.tol, floor2, sub);
       }
       __syncthreads();
@@ -186,34 +189,12 @@ __global__ void __launch_bounds__(1024) jacobi_kernel(JacobiArgs p, double2* __r
   // write back
   for (int v = warp; v < 2 * b; v += nwarps) {
     const int row = (v < b) ? I * b + v : J * b + (v - b);
-    if (row < p.n) {
+    if (row < nrows) {
       double2* dst = Y + (long long)row * p.ld;
       const double2* src = smem + v * mt;
       for (int k = lane; k < mt; k += 32) dst[k] = src[k];
     }
   }
-}
-
-// Device-wide barrier between the CTAs that work on one matrix (grid.x of them; the kernel is launched
-// cooperatively, so they are co-resident). `bar` only ever increases: round `phase` completes at (phase+1)*nblk.
-__device__ __forceinline__ void matrix_barrier(unsigned* bar, unsigned nblk, unsigned& phase, int* errflag) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
-    const unsigned target = (phase + 1u) * nblk;
-    unsigned spins = 0;
-    while (*((volatile unsigned*)bar) < target) {
-      __nanosleep(40);
-      if (++spins > (1u << 26)) {  // ~seconds: never expected; refuse to hang the device
-        *errflag = 1;
-        break;
-      }
-    }
-    __threadfence();
-  }
-  __syncthreads();
-  ++phase;
 }
 
 // Persistent variant for matrices that span several block pairs: one cooperative launch runs every round of every
@@ -235,17 +216,23 @@ __global__ void __launch_bounds__(1024) jacobi_persistent_kernel(JacobiArgs p, d
   int* errflag = cnt + 35;
   unsigned phase = 0;
   double2* Y = Yall + (long long)bidx * p.batchStride;
+  const int nrows = p.rank ? min(p.n, p.rank[(long long)bidx * p.rankStride]) : p.n;
+  if (nrows < 2) return;   // uniform over the CTAs of this matrix: nobody reaches a barrier
+  // only the blocks that hold non-zero rows take part in the tournament
+  const int nbp = (((nrows + b - 1) / b) + 1) & ~1;
+  const unsigned ncta = (unsigned)(nbp / 2);
+  if (blockIdx.x >= ncta) return;
   const int be = (b + 1) & ~1;
   const int half = be / 2;
 
   for (int sw = 0; sw < p.maxSweeps; ++sw) {
-    for (int round = 0; round < p.nbp - 1; ++round) {
+    for (int round = 0; round < nbp - 1; ++round) {
       int I, J;
-      rr_pair(p.nbp, round, blockIdx.x, I, J);
+      rr_pair(nbp, round, blockIdx.x, I, J);
       for (int v = warp; v < 2 * b; v += nwarps) {  // stage (L2 reads: other SMs wrote these rows last round)
         const int row = (v < b) ? I * b + v : J * b + (v - b);
         double2* dst = smem + v * mt;
-        if (row < p.n) {
+        if (row < nrows) {
           const double2* src = Y + (long long)row * p.ld;
           for (int k = lane; k < mt; k += 32) dst[k] = __ldcg(src + k);
         }
@@ -260,7 +247,7 @@ __global__ void __launch_bounds__(1024) jacobi_persistent_kernel(JacobiArgs p, d
             int a0, a1;
             rr_pair(be, step, q - blk * half, a0, a1);
             const int first = (blk ? J : I) * b;
-            const bool active = q < be && a0 < b && a1 < b && first + a0 < p.n && first + a1 < p.n;
+            const bool active = q < be && a0 < b && a1 < b && first + a0 < nrows && first + a1 < nrows;
             rot |= rotate_pair<G>(smem + (blk * b + a0) * mt, smem + (blk * b + a1) * mt, active, p.m, mt, p.tol,
                                   floor2, sub);
           }
@@ -272,21 +259,21 @@ __global__ void __launch_bounds__(1024) jacobi_persistent_kernel(JacobiArgs p, d
           const int q = base + slot;
           int a1 = q + step;
           if (a1 >= b) a1 -= b;
-          const bool active = q < b && I * b + q < p.n && J * b + a1 < p.n;
+          const bool active = q < b && I * b + q < nrows && J * b + a1 < nrows;
           rot |= rotate_pair<G>(smem + q * mt, smem + (b + a1) * mt, active, p.m, mt, p.tol, floor2, sub);
         }
         __syncthreads();
       }
       for (int v = warp; v < 2 * b; v += nwarps) {  // write back
         const int row = (v < b) ? I * b + v : J * b + (v - b);
-        if (row < p.n) {
+        if (row < nrows) {
           double2* dst = Y + (long long)row * p.ld;
           const double2* src = smem + v * mt;
           for (int k = lane; k < mt; k += 32) dst[k] = src[k];
         }
       }
       if (rot && sub == 0) atomicAdd(&cnt[sw], 1);
-      matrix_barrier(bar, gridDim.x, phase, errflag);
+      matrix_barrier(bar, ncta, phase, errflag);
     }
     if (*((volatile int*)&cnt[sw]) == 0 || *((volatile int*)errflag)) break;
   }
@@ -348,7 +335,7 @@ __global__ void __launch_bounds__(256) rows_finalize_kernel(int n, int m, int mz
       rk += (w > v) || (w == v && q < r);
     }
     rank[r] = rk;
-    sOut[(long long)bidx * n + rk] = v;
+    sOut[(long long)bidx * n + rk] = (normalize & 2) ? v * v : v;
   }
   __syncthreads();
   double vmax = 0;
@@ -359,7 +346,7 @@ __global__ void __launch_bounds__(256) rows_finalize_kernel(int n, int m, int mz
     const double nv = norms[r];
     if (Yn) {
       double sc = 1.0;
-      if (normalize) sc = (nv > zeroTol * vmax && nv > 0) ? 1.0 / nv : 0.0;
+      if (normalize & 1) sc = (nv > zeroTol * vmax && nv > 0) ? 1.0 / nv : 0.0;
       double2* dst = Yn + ((long long)bidx * n + rk) * m;
       for (int k = lane; k < m; k += 32) {
         double2 u = row[k];
@@ -398,9 +385,9 @@ __global__ void __launch_bounds__(256) rows_setup_kernel(int n, int m, const dou
 
 }  // namespace mpdo
 
-extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t batchStride, void* Y, double tol,
-                                int maxSweeps, int32_t* work, void* stream) {
-  using namespace mpdo;
+namespace mpdo {
+int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchStride, void* Y, double tol,
+                       int maxSweeps, int32_t* work, const int* rank, int rankStride, void* stream) {
   if (batch <= 0 || n <= 0) return 0;
   if (!Y || !work || m <= 0 || mt < m || ld < mt) return fail(MPDO_EINVAL, "mpdo_jacobi_rows: bad argument");
   if (maxSweeps < 1) maxSweeps = 1;
@@ -458,6 +445,8 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
   a.maxSweeps = maxSweeps;
   a.tol = tol;
   a.cnt = work;
+  a.rank = rank;
+  a.rankStride = rankStride;
   const size_t smem = (size_t)(2 * b) * rowBytes;
   // lanes per row pair: short rows share a warp between several pairs (see rotate_pair)
   int G = mt >= 384 ? 32 : 16;   // (8 / 16 / 32 measured on n = 24, 48, 96: 16 is best or equal up to mt = 192)
@@ -531,6 +520,12 @@ extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t
     if (!any) break;
   }
   return 0;
+}
+}  // namespace mpdo
+
+extern "C" int mpdo_jacobi_rows(int batch, int n, int m, int mt, int ld, int64_t batchStride, void* Y, double tol,
+                                int maxSweeps, int32_t* work, void* stream) {
+  return mpdo::jacobi_rows_ranked(batch, n, m, mt, ld, batchStride, Y, tol, maxSweeps, work, nullptr, 0, stream);
 }
 
 extern "C" int mpdo_rows_finalize(int batch, int n, int m, int mz, int ld, int64_t batchStride, const void* Y,
