@@ -60,6 +60,8 @@ typedef struct {
   int32_t acc64;                  /* 1: accumulate in fp64 (always when any operand is c128) */
   int32_t a_kfast, b_jfast;       /* loader hints: which axis of A / B is contiguous */
   int32_t ksplit;                 /* >1: split K over CTAs, atomically accumulated (C must be pre-zeroed or beta==1) */
+  int32_t hermitian;              /* 1: the result is Hermitian (a Gram matrix; M == N, beta == 0): only the tiles on and
+                                     below the diagonal are computed, the rest is written as the conjugate mirror */
   double alpha, beta;
   mpdo_idxmap Ab, Ai, Ak;
   mpdo_idxmap Bb, Bk, Bj;

@@ -25,7 +25,8 @@ class CpuPrims:
     def launch_count(self):
         return self.calls
 
-    def contract(self, A, ra, B, rb, Cv, rc, conjA=False, conjB=False, acc64=None, alpha=1.0, beta=0.0):
+    def contract(self, A, ra, B, rb, Cv, rc, conjA=False, conjB=False, acc64=None, alpha=1.0, beta=0.0,
+                 hermitian=False):
         self.calls += 1
         nb, ni, nk = ra
         batch = _prod(A.shape[:nb])

@@ -62,6 +62,23 @@ def test_contract_gram_kappa_axis(cuda_prims, dt, tol):
     c, g = both(f, cuda_prims, T)
     assert (g.cpu() - c).abs().max() <= tol * c.abs().max().item()
 
+@pytest.mark.parametrize('dt,tol', [(C64, 1e-6), (C128, 1e-12)])
+@pytest.mark.parametrize('n,K,Bn', [(10, 40, 2), (64, 16, 1), (130, 700, 2), (200, 64, 3), (513, 96, 1)])
+def test_contract_hermitian_gram(cuda_prims, dt, tol, n, K, Bn):
+    """hermitian=1 computes the tiles on/below the diagonal and mirrors them; with and without split-K."""
+    X = rnd((Bn, K, n), dt, 8)
+
+    def f(p, X):
+        G = torch.zeros((Bn, n, n), dtype=C128, device=X.device)
+        return p.contract(X.permute(0, 2, 1), (1, 1, 1), X, (1, 1, 1), G, (1, 1, 1), conjA=True, acc64=True,
+                          hermitian=True)
+
+    c, g = both(f, cuda_prims, X)
+    g = g.cpu()
+    assert (g - c).abs().max() <= tol * c.abs().max().item()
+    assert (g - g.mH).abs().max() <= 1e-13 * c.abs().max().item()
+
+
 
 def test_contract_splitk_and_broadcast(cuda_prims):
     # long K with few tiles triggers the split-K path; A broadcast over batch with stride 0

@@ -21,7 +21,7 @@ class ContractDesc(C.Structure):
         ('M', C.c_int32), ('N', C.c_int32), ('K', C.c_int32), ('batch', C.c_int32),
         ('dtypeA', C.c_int32), ('dtypeB', C.c_int32), ('dtypeC', C.c_int32),
         ('conjA', C.c_int32), ('conjB', C.c_int32), ('acc64', C.c_int32),
-        ('a_kfast', C.c_int32), ('b_jfast', C.c_int32), ('ksplit', C.c_int32),
+        ('a_kfast', C.c_int32), ('b_jfast', C.c_int32), ('ksplit', C.c_int32), ('hermitian', C.c_int32),
         ('alpha', C.c_double), ('beta', C.c_double),
         ('Ab', IdxMap), ('Ai', IdxMap), ('Ak', IdxMap),
         ('Bb', IdxMap), ('Bk', IdxMap), ('Bj', IdxMap),

@@ -94,15 +94,17 @@ class CudaPrims:
         return int(self.lib.mpdo_launch_count())
 
     # -- contraction --------------------------------------------------------------------------------
-    def contract(self, A, ra, B, rb, Cv, rc, conjA=False, conjB=False, acc64=None, alpha=1.0, beta=0.0):
-        """Cv[b,i,j] = alpha * sum_k op(A[b,i,k]) op(B[b,k,j]) + beta * Cv[b,i,j] on strided views."""
+    def contract(self, A, ra, B, rb, Cv, rc, conjA=False, conjB=False, acc64=None, alpha=1.0, beta=0.0,
+                 hermitian=False):
+        """Cv[b,i,j] = alpha * sum_k op(A[b,i,k]) op(B[b,k,j]) + beta * Cv[b,i,j] on strided views.
+        hermitian: the caller guarantees a Hermitian result (Gram matrix): half of the tiles are computed."""
         # descriptors depend only on the geometry of the three views: cache them (the same few dozen geometries
         # recur in every layer, and building one costs more host time than launching the kernel)
         key = (A.shape, A.stride(), A.dtype, ra, B.shape, B.stride(), B.dtype, rb, Cv.shape, Cv.stride(), Cv.dtype, rc,
-               conjA, conjB, acc64, alpha, beta)
+               conjA, conjB, acc64, alpha, beta, hermitian)
         hit = self._desc_cache.get(key)
         if hit is None:
-            hit = self._build_desc(A, ra, B, rb, Cv, rc, conjA, conjB, acc64, alpha, beta)
+            hit = self._build_desc(A, ra, B, rb, Cv, rc, conjA, conjB, acc64, alpha, beta, hermitian)
             if len(self._desc_cache) < 4096:
                 self._desc_cache[key] = hit
         d, ksplit = hit
@@ -115,7 +117,7 @@ class CudaPrims:
                    'mpdo_contract')
         return Cv
 
-    def _build_desc(self, A, ra, B, rb, Cv, rc, conjA, conjB, acc64, alpha, beta):
+    def _build_desc(self, A, ra, B, rb, Cv, rc, conjA, conjB, acc64, alpha, beta, hermitian=False):
         (ab, ai, ak), (bb, bk, bj), (cb, ci, cj) = split_roles(A, ra), split_roles(B, rb), split_roles(Cv, rc)
         M, K, N = _prod(ai[0]), _prod(ak[0]), _prod(bj[0])
         batch = _prod(ab[0])
@@ -135,7 +137,9 @@ class CudaPrims:
         inner = lambda lv: lv[-1][1] if lv else 1 << 60
         d.a_kfast = int(inner(lak) <= inner(lai))
         d.b_jfast = int(inner(lbj) <= inner(lbk))
-        tiles = ((M + 63) // 64) * ((N + 63) // 64) * batch
+        tm = (M + 63) // 64
+        tiles = (tm * (tm + 1) // 2 if hermitian else tm * ((N + 63) // 64)) * batch
+        d.hermitian = int(bool(hermitian))
         ksplit = 1
         if K >= 256 and tiles < self.sm_count and Cv.is_contiguous() and beta in (0.0, 1.0):
             ksplit = max(1, min((K + 63) // 64, (2 * self.sm_count) // max(tiles, 1)))

@@ -53,7 +53,7 @@ class Engine:
         for d in X.shape[:nb]:
             Bn *= d
         G = self._empty((Bn, n, n), X, C128)
-        self.p.contract(At, (nb, nc, nr), X, (nb, nr, nc), G, (1, 1, 1), conjA=True, acc64=True)
+        self.p.contract(At, (nb, nc, nr), X, (nb, nr, nc), G, (1, 1, 1), conjA=True, acc64=True, hermitian=True)
         return G
 
     def _gram_rows(self, M, roles):
@@ -68,7 +68,7 @@ class Engine:
         for d in M.shape[:nb]:
             Bn *= d
         G = self._empty((Bn, n, n), M, C128)
-        self.p.contract(M, (nb, nr, nc), Mt, (nb, nc, nr), G, (1, 1, 1), conjB=True, acc64=True)
+        self.p.contract(M, (nb, nr, nc), Mt, (nb, nc, nr), G, (1, 1, 1), conjB=True, acc64=True, hermitian=True)
         return G
 
     def orth_cols(self, X, roles):
@@ -294,7 +294,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------
     # R3: inner-index (kappa) truncation                 TNNOptimizer.py:164-197
     # ------------------------------------------------------------------------------------------
-    def eigh_topk(self, G, k, max_iter=40):
+    def eigh_topk(self, G, k, max_iter=None):
         """Leading k eigenpairs of Hermitian PSD G [B,n,n] (complex128) by block subspace iteration with
         Rayleigh-Ritz, iterated until the residuals |G v - theta v| of the k kept pairs are at rounding level
         (this is an exact solver run to convergence, unlike the reference's three un-orthonormalised power
@@ -316,6 +316,8 @@ class Engine:
         Gt = G.permute(0, 2, 1)
         Zr = torch.empty((Bn, blk, n), dtype=C128, device=G.device)
         p.contract(Yr, (1, 1, 1), Gt, (1, 1, 1), Zr, (1, 1, 1))
+        if max_iter is None:   # short leash: the caller's full decomposition is the better policy for stalled clusters
+            max_iter = 6 if self.f32 else 12
         for it in range(max_iter):
             # orthonormalise the rows of Zr
             H = self._gram_rows(Zr, (1, 1, 1))

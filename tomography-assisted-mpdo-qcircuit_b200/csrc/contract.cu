@@ -32,10 +32,21 @@ __global__ void __launch_bounds__(NT) contract_kernel(const mpdo_contract_desc d
   const int tx = tid % 16, ty = tid / 16;
 
   long long t = blockIdx.x;
-  const int tn = (int)(t % tilesN);
-  t /= tilesN;
-  const int tm = (int)(t % tilesM);
-  t /= tilesM;
+  int tm, tn;
+  if (d.hermitian) {   // tiles on and below the diagonal, enumerated row by row: index = tm (tm + 1) / 2 + tn
+    const int tri = tilesM * (tilesM + 1) / 2;
+    const int ti = (int)(t % tri);
+    t /= tri;
+    tm = (int)((sqrtf(8.0f * (float)ti + 1.0f) - 1.0f) * 0.5f);
+    while (tm * (tm + 1) / 2 > ti) --tm;
+    while ((tm + 1) * (tm + 2) / 2 <= ti) ++tm;
+    tn = ti - tm * (tm + 1) / 2;
+  } else {
+    tn = (int)(t % tilesN);
+    t /= tilesN;
+    tm = (int)(t % tilesM);
+    t /= tilesM;
+  }
   const int ksplit = d.ksplit > 1 ? d.ksplit : 1;
   const int ks = (int)(t % ksplit);
   const int b = (int)(t / ksplit);
@@ -186,6 +197,18 @@ __global__ void __launch_bounds__(NT) contract_kernel(const mpdo_contract_desc d
         o.y = (RC)im;
         *p = o;
       }
+      if (d.hermitian && tm != tn) {   // mirror: C[j,i] = conj(C[i,j])
+        TC* q = Cb + map_idx(d.Ci, j0 + tx + 16 * v) + map_idx(d.Cj, i);
+        if (ksplit > 1) {
+          atomicAdd(&q->x, (RC)re);
+          atomicAdd(&q->y, (RC)(-im));
+        } else {
+          TC o;
+          o.x = (RC)re;
+          o.y = (RC)(-im);
+          *q = o;
+        }
+      }
     }
   }
 }
@@ -196,7 +219,8 @@ static int launch_contract(const mpdo_contract_desc& d, const void* A, const voi
   const int ksplit = d.ksplit > 1 ? d.ksplit : 1;
   int kChunk = (d.K + ksplit - 1) / ksplit;
   kChunk = ((kChunk + BK - 1) / BK) * BK;
-  long long grid = (long long)tilesM * tilesN * ksplit * d.batch;
+  const long long tilesMN = d.hermitian ? (long long)tilesM * (tilesM + 1) / 2 : (long long)tilesM * tilesN;
+  long long grid = tilesMN * ksplit * d.batch;
   if (grid <= 0) return 0;
   if (grid > 2147483647LL) return fail(MPDO_EINVAL, "mpdo_contract: grid too large");
   {
@@ -218,6 +242,8 @@ extern "C" int mpdo_contract(const mpdo_contract_desc* dp, const void* A, const 
   const mpdo_contract_desc& d = *dp;
   if (d.M < 0 || d.N < 0 || d.K < 0 || d.batch < 0) return fail(MPDO_EINVAL, "mpdo_contract: negative extent");
   if (d.M == 0 || d.N == 0 || d.batch == 0) return 0;
+  if (d.hermitian && (d.M != d.N || d.beta != 0.0))
+    return fail(MPDO_EINVAL, "mpdo_contract: hermitian needs M == N and beta == 0");
   cudaStream_t st = (cudaStream_t)stream;
   const int key = (d.dtypeA << 2) | (d.dtypeB << 1) | d.dtypeC;
   const bool f64 = d.acc64 || key != 0;

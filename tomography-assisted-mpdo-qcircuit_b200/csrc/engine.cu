@@ -7,6 +7,7 @@
 // is the production path: one C call per step instead of ~50 Python-level launches, which is what bounds a layer
 // once the kernels themselves take tens of microseconds.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -79,7 +80,7 @@ static int sm_count() {
 }
 
 int contract(cudaStream_t st, const Tn& A, Roles ra, const Tn& B, Roles rb, const Tn& C, Roles rc, bool conjA,
-             bool conjB, int acc64, double alpha, double beta) {
+             bool conjB, int acc64, double alpha, double beta, bool hermitian) {
   mpdo_contract_desc d;
   memset(&d, 0, sizeof(d));
   const long long M = prod(A, ra.nb, ra.n1), K = prod(A, ra.nb + ra.n1, ra.n2);
@@ -112,7 +113,9 @@ int contract(cudaStream_t st, const Tn& A, Roles ra, const Tn& B, Roles rb, cons
   auto inner = [](const Level* lv, int k) { return k ? lv[k - 1].s : (1LL << 60); };
   d.a_kfast = inner(lak, nak) <= inner(lai, nai);
   d.b_jfast = inner(lbj, nbj) <= inner(lbk, nbk);
-  const long long tiles = ((M + 63) / 64) * ((N + 63) / 64) * batch;
+  const long long tm_ = (M + 63) / 64;
+  const long long tiles = (hermitian ? tm_ * (tm_ + 1) / 2 : tm_ * ((N + 63) / 64)) * batch;
+  d.hermitian = hermitian ? 1 : 0;
   int ksplit = 1;
   const int sms = sm_count();
   // Gram matrices of the sweeps are one or two output tiles with a long K: a single CTA walking K alone is pure
@@ -346,7 +349,7 @@ static int gram_cols(Ctx& c, const Tn& X, Roles r, Tn* G) {
   const long long B = prod(X, 0, r.nb), n = prod(X, r.nb + r.n1, r.n2);
   *G = c.ar.alloc(MPDO_C128, {B, n, n});
   ARENA_OK(c);
-  return contract(c.st, swap_groups(X, r), {r.nb, r.n2, r.n1}, X, r, *G, {1, 1, 1}, true, false, 1);
+  return contract(c.st, swap_groups(X, r), {r.nb, r.n2, r.n1}, X, r, *G, {1, 1, 1}, true, false, 1, 1.0, 0.0, true);
 }
 
 // G[b,i,i'] = sum_cols M[b,i,cols] conj(M[b,i',cols])
@@ -354,7 +357,7 @@ static int gram_rows(Ctx& c, const Tn& M, Roles r, Tn* G) {
   const long long B = prod(M, 0, r.nb), n = prod(M, r.nb, r.n1);
   *G = c.ar.alloc(MPDO_C128, {B, n, n});
   ARENA_OK(c);
-  return contract(c.st, M, r, swap_groups(M, r), {r.nb, r.n2, r.n1}, *G, {1, 1, 1}, false, true, 1);
+  return contract(c.st, M, r, swap_groups(M, r), {r.nb, r.n2, r.n1}, *G, {1, 1, 1}, false, true, 1, 1.0, 0.0, true);
 }
 
 static Tn transposed(const Tn& X) { return X.permute({0, 2, 1}); }  // [B,a,b] -> [B,b,a] view
@@ -517,7 +520,10 @@ static int eigh_topk(Ctx& c, const Tn& G, int k, double** theta_out, Tn* Vt, int
     hcap = B;
   }
   *converged = 0;
-  for (int it = 0; it < 40; ++it) {
+  // Near-degenerate clusters at the cut (e.g. the equal-weight error branches of a chi-matrix gate) make the
+  // iteration stall; the rank-revealing full decomposition is cheap enough that a short leash is the better policy.
+  const int maxIter = c.f32 ? 6 : 12;
+  for (int it = 0; it < maxIter; ++it) {
     Tn H, Uh, Fo, Bm, Wh, ts;
     double *lam, *theta;
     EC(gram_rows(c, Zr, {1, 1, 1}, &H));
@@ -551,6 +557,8 @@ static int eigh_topk(Ctx& c, const Tn& G, int k, double** theta_out, Tn* Vt, int
     Yr = Y3;
     Zr = Z3;
     if (worst <= tol) {
+      static const bool trace = getenv("MPDO_TRACE") != nullptr;
+      if (trace) fprintf(stderr, "[mpdo] eigh_topk n=%lld k=%d blk=%d B=%lld iterations=%d\n", n, k, blk, B, it + 1);
       *converged = 1;
       *theta_out = theta;   // stride blk
       *Vt = Y3;             // [B, blk, n]; the first k rows are the kept vectors

@@ -133,7 +133,7 @@ struct Arena {  // scratch buffers freed (stream-ordered) when the step returns
 };
 
 int contract(cudaStream_t st, const Tn& A, Roles ra, const Tn& B, Roles rb, const Tn& C, Roles rc, bool conjA = false,
-             bool conjB = false, int acc64 = -1, double alpha = 1.0, double beta = 0.0);
+             bool conjB = false, int acc64 = -1, double alpha = 1.0, double beta = 0.0, bool hermitian = false);
 
 }  // namespace eng
 }  // namespace mpdo

@@ -28,3 +28,9 @@ for (n, m), c in sorted(hist.items()):
     tot += cost
     print('n=%4d m=%4d count=%4d  ~%.1f GFLOP' % (n, m, c, cost))
 print('total ~%.0f GFLOP' % tot)
+topk = collections.Counter()
+for l in lines:
+    m = re.search(r'eigh_topk n=(\d+) k=(\d+) blk=(\d+) B=(\d+) iterations=(\d+)', l)
+    if m: topk[tuple(int(x) for x in m.groups())] += 1
+for key, c in sorted(topk.items()):
+    print('eigh_topk n=%d k=%d blk=%d B=%d iterations=%d: count %d' % (key + (c,)))
