@@ -226,7 +226,6 @@ def b200_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    lib.mpdo_timing_enable(1)   # CUDA events around every contraction / Jacobi launch, on the launching stream
     launches0 = base.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -246,6 +245,21 @@ def b200_arm(args):
     launches = base.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     secs = ev0.elapsed_time(ev1) * 1e-3
+    bond_dims = [int(s.data.shape[4]) for s in state[:-1]]
+
+    # ---- roofline leg: the same K layers replayed from the same state with CUDA events around every launch of the
+    # library (on the launching stream). Kept out of the `value` / `e2e` passes: ~2 x 1800 event records per step,
+    # issued from a dozen strand threads, slow the step itself by 1.5x (measured), which would make the headline a
+    # measurement of the instrumentation.
+    for s, snap in zip(state, snapshot):
+        s.data = snap.clone()
+    lib.mpdo_timing_enable(1)
+    barrier()
+    for d in range(P + W, P + W + K):
+        flush.zero_()
+        circuits[d][0].evolve(state)
+    barrier()
+
     def timing(cls, min_flops=0.0):
         import ctypes as C
         sec, fl, by, mxs, mxf = (C.c_double() for _ in range(5))
@@ -255,9 +269,8 @@ def b200_arm(args):
         return {'seconds': sec.value, 'flops': fl.value, 'bytes': by.value, 'launches': n.value,
                 'largest_seconds': mxs.value, 'largest_flops': mxf.value}
 
-    t_contract, t_big, t_jacobi = timing(0), timing(0, 2e9), timing(1)
+    t_contract, t_big, t_jacobi, t_chol = timing(0), timing(0, 2e9), timing(1), timing(2)
     lib.mpdo_timing_enable(0)
-    bond_dims = [int(s.data.shape[4]) for s in state[:-1]]
 
     # ---- e2e: host buffers in, host buffers out, every step -------------------------------------------
     # one pinned staging buffer per site, sized for the largest site tensor the truncated state can have
@@ -265,7 +278,7 @@ def b200_arm(args):
     pinned = [torch.empty(cap, dtype=torch.complex64, pin_memory=True) for _ in state]
     shapes = [tuple(s.data.shape) for s in state]
     for s, snap in zip(state, snapshot):
-        s.data = snap
+        s.data = snap.clone()
     shapes = [tuple(s.data.shape) for s in state]
     for s, pb in zip(state, pinned):
         pb[:s.data.numel()].copy_(s.data.reshape(-1))
@@ -332,17 +345,26 @@ def b200_arm(args):
             'largest_launch': {'GFLOP': t_contract['largest_flops'] / 1e9, 'ms': t_contract['largest_seconds'] * 1e3,
                                'TFLOP/s': t_contract['largest_flops'] / max(t_contract['largest_seconds'], 1e-30) / 1e12},
             'note': 'algorithmic flops = 8*M*N*K per complex contraction (SURVEY 8d), every launch timed with CUDA '
-                    'events on its own stream inside the timed region; the denominator is the dense bf16 tensor peak '
-                    'although the kernel must deliver fp32/fp64-accurate complex arithmetic on small cores. The '
-                    'dominant kernel of this workload by device time is the Jacobi kernel (see dominant_kernel).',
+                    'events on its own stream in a replay of the timed layers from the same state (the value / e2e '
+                    'passes run without the per-launch events); the denominator is the dense bf16 tensor peak although '
+                    'the kernel must deliver fp32/fp64-accurate complex arithmetic (FFMA/DFMA), most of it fp64-'
+                    'accumulated Gram matrices. Device time is split between this kernel and the two latency-bound '
+                    'factorisation kernels (see factorisation_kernels).',
         }
         jt = max(t_jacobi['seconds'], 1e-30)
-        roof['share_of_step_device_time'] = ct / (ct + jt)
+        ht = max(t_chol['seconds'], 1e-30)
+        roof['share_of_step_device_time'] = ct / (ct + jt + ht)
         dominant = {
-            'kernel': 'jacobi_kernel (one-sided Jacobi on fp64 rows in shared memory)',
-            'launches': t_jacobi['launches'], 'kernel_seconds': jt, 'avg_launch_us': 1e6 * jt / max(t_jacobi['launches'], 1),
-            'share_of_timed_device_seconds': jt / (ct + jt),
-            'bound': 'instruction issue / shared-memory latency on 1-16 SMs per decomposition (ncu: profiles/)',
+            'jacobi': {'kernel': 'jacobi_kernel / jacobi_persistent_kernel (one-sided Jacobi on fp64 rows in shared memory)',
+                       'launches': t_jacobi['launches'], 'kernel_seconds': jt,
+                       'avg_launch_us': 1e6 * jt / max(t_jacobi['launches'], 1),
+                       'share_of_timed_device_seconds': jt / (ct + jt + ht)},
+            'cholesky': {'kernel': 'chol_kernel (rank-revealing pivoted Cholesky, rows of L resident in shared memory)',
+                         'launches': t_chol['launches'], 'kernel_seconds': ht,
+                         'avg_launch_us': 1e6 * ht / max(t_chol['launches'], 1),
+                         'share_of_timed_device_seconds': ht / (ct + jt + ht)},
+            'bound': 'latency: one device-wide barrier per tournament round / pivot step on 1-64 SMs per matrix '
+                     '(ncu: profiles/)',
             'note': 'kernel seconds are summed over concurrent streams, so they can exceed the wall time of the step',
         }
         cpu = None
@@ -363,7 +385,7 @@ def b200_arm(args):
                        'bond_dims_after_timed_region': bond_dims},
             'e2e': {'value': tot_e2e_updates / e2e_secs, 'unit': UNIT, 'h2d_bytes_per_step': h2d // K,
                     'd2h_bytes_per_step': d2h // K, 'ms_per_step': 1e3 * e2e_secs / K},
-            'gpu_launches': int(tot_launches), 'clocks': clocks, 'roofline': roof, 'dominant_kernel': dominant,
+            'gpu_launches': int(tot_launches), 'clocks': clocks, 'roofline': roof, 'factorisation_kernels': dominant,
             'cpu_baseline': cpu,
         }
         print(json.dumps(line), flush=True)

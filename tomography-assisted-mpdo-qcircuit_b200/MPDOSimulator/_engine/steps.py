@@ -318,6 +318,7 @@ class Engine:
         p.contract(Yr, (1, 1, 1), Gt, (1, 1, 1), Zr, (1, 1, 1))
         if max_iter is None:   # short leash: the caller's full decomposition is the better policy for stalled clusters
             max_iter = 6 if self.f32 else 12
+        prev_worst = float('inf')
         for it in range(max_iter):
             # orthonormalise the rows of Zr
             H = self._gram_rows(Zr, (1, 1, 1))
@@ -345,6 +346,9 @@ class Engine:
             self.stats['topk_iters'] = it + 1
             if worst <= tol:
                 return theta[:, :k].contiguous(), Yr[:, :k, :].contiguous()
+            if it >= 1 and worst > 0.05 * prev_worst:   # stalled: the cut sits inside a cluster wider than the block
+                return None
+            prev_worst = worst
         return None
 
     def kappa_truncate(self, T, kappa, max_err=None):

@@ -523,6 +523,7 @@ static int eigh_topk(Ctx& c, const Tn& G, int k, double** theta_out, Tn* Vt, int
   // Near-degenerate clusters at the cut (e.g. the equal-weight error branches of a chi-matrix gate) make the
   // iteration stall; the rank-revealing full decomposition is cheap enough that a short leash is the better policy.
   const int maxIter = c.f32 ? 6 : 12;
+  double prevWorst = 1e300;
   for (int it = 0; it < maxIter; ++it) {
     Tn H, Uh, Fo, Bm, Wh, ts;
     double *lam, *theta;
@@ -556,6 +557,9 @@ static int eigh_topk(Ctx& c, const Tn& G, int k, double** theta_out, Tn* Vt, int
     for (long long i = 0; i < B; ++i) worst = std::max(worst, hres[i]);
     Yr = Y3;
     Zr = Z3;
+    // stalled (less than 20x per iteration): the cut sits inside a cluster wider than the block; stop paying for it
+    if (it >= 1 && worst > tol && worst > 0.05 * prevWorst) return 0;
+    prevWorst = worst;
     if (worst <= tol) {
       static const bool trace = getenv("MPDO_TRACE") != nullptr;
       if (trace) fprintf(stderr, "[mpdo] eigh_topk n=%lld k=%d blk=%d B=%lld iterations=%d\n", n, k, blk, B, it + 1);

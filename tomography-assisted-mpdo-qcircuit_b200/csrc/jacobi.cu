@@ -279,6 +279,152 @@ __global__ void __launch_bounds__(1024) jacobi_persistent_kernel(JacobiArgs p, d
   }
 }
 
+// Rotation of a register-resident row x (E entries per lane, entry k = lane + 32 e) against a row y in shared
+// memory: y is streamed twice (inner products, then the update) and x never leaves the register file, which halves
+// the shared-memory traffic of rotate_pair (3 row passes instead of 6). One warp per pair; `active` is warp-uniform.
+template <int E>
+__device__ __forceinline__ int rotate_reg(double2 (&x)[E], double2* __restrict__ y, bool active, int m, int mt,
+                                          double tol, double floor2, int lane) {
+  if (!active) return 0;
+  double a = 0, bq = 0, gr = 0, gi = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int k = lane + 32 * e;
+    if (k < m) {
+      const double2 u = x[e], v = y[k];
+      a = fma(u.x, u.x, fma(u.y, u.y, a));
+      bq = fma(v.x, v.x, fma(v.y, v.y, bq));
+      gr = fma(u.x, v.x, fma(u.y, v.y, gr));
+      gi = fma(u.y, v.x, fma(-u.x, v.y, gi));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    bq += __shfl_xor_sync(0xffffffffu, bq, o);
+    gr += __shfl_xor_sync(0xffffffffu, gr, o);
+    gi += __shfl_xor_sync(0xffffffffu, gi, o);
+  }
+  const double g2 = gr * gr + gi * gi;
+  const double ab = a * bq;
+  if (!(ab > floor2) || !(g2 > tol * tol * ab)) return 0;
+  const double d = 0.5 * (bq - a);
+  const double ad = fabs(d);
+  const double h = sqrt(fma(d, d, g2));
+  const double ru = rsqrt(2.0 * h * (h + ad));
+  const double c = (h + ad) * ru;
+  const double sg = d >= 0 ? ru : -ru;
+  const double sr = sg * gr, si = sg * gi;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int k = lane + 32 * e;
+    if (k < mt) {
+      const double2 u = x[e], v = y[k];
+      double2 xn, yn;
+      xn.x = c * u.x - (sr * v.x - si * v.y);
+      xn.y = c * u.y - (sr * v.y + si * v.x);
+      yn.x = (sr * u.x + si * u.y) + c * v.x;
+      yn.y = (sr * u.y - si * u.x) + c * v.y;
+      x[e] = xn;
+      y[k] = yn;
+    }
+  }
+  return 1;
+}
+
+// Persistent kernel with register-resident rows for long rows (mt <= 32 E): during the cross-pair steps of a round
+// warp q keeps row q of block I in registers and meets the rows of block J one after the other in shared memory.
+template <int E, int MAXT>
+__global__ void __launch_bounds__(MAXT) jacobi_persistent_reg_kernel(JacobiArgs p, double2* __restrict__ Yall) {
+  extern __shared__ double2 smem[];
+  const int bidx = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;   // nwarps == b
+  const int b = p.b, mt = p.mt;
+  int* cnt = p.cnt + (long long)bidx * WORK_INTS;
+  const double amax = *reinterpret_cast<const double*>(cnt + 32);
+  const double floor2 = fmax(1e-290, 1e-48 * amax * amax);
+  unsigned* bar = reinterpret_cast<unsigned*>(cnt + 34);
+  int* errflag = cnt + 35;
+  unsigned phase = 0;
+  double2* Y = Yall + (long long)bidx * p.batchStride;
+  const int nrows = p.rank ? min(p.n, p.rank[(long long)bidx * p.rankStride]) : p.n;
+  if (nrows < 2) return;
+  const int nbp = (((nrows + b - 1) / b) + 1) & ~1;
+  const unsigned ncta = (unsigned)(nbp / 2);
+  if (blockIdx.x >= ncta) return;
+  const int be = (b + 1) & ~1;
+  const int half = be / 2;
+
+  for (int sw = 0; sw < p.maxSweeps; ++sw) {
+    for (int round = 0; round < nbp - 1; ++round) {
+      int I, J;
+      rr_pair(nbp, round, blockIdx.x, I, J);
+      for (int v = warp; v < 2 * b; v += nwarps) {
+        const int row = (v < b) ? I * b + v : J * b + (v - b);
+        double2* dst = smem + v * mt;
+        if (row < nrows) {
+          const double2* src = Y + (long long)row * p.ld;
+          for (int k = lane; k < mt; k += 32) dst[k] = __ldcg(src + k);
+        }
+      }
+      __syncthreads();
+      int rot = 0;
+      if (round == 0) {   // pairs inside each block: both rows in shared memory
+        for (int step = 0; step < be - 1; ++step) {
+          for (int base = 0; base < be; base += nwarps) {
+            const int q = base + warp;
+            const int blk = q >= half ? 1 : 0;
+            int a0, a1;
+            rr_pair(be, step, q - blk * half, a0, a1);
+            const int first = (blk ? J : I) * b;
+            const bool active = q < be && a0 < b && a1 < b && first + a0 < nrows && first + a1 < nrows;
+            rot |= rotate_pair<32>(smem + (blk * b + a0) * mt, smem + (blk * b + a1) * mt, active, p.m, mt, p.tol,
+                                   floor2, lane);
+          }
+          __syncthreads();
+        }
+      }
+      // cross pairs: warp q holds row q of block I
+      const bool mine = warp < b && I * b + warp < nrows;
+      double2 x[E];
+      {
+        const double2* xr = smem + warp * mt;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int k = lane + 32 * e;
+          x[e] = (mine && k < mt) ? xr[k] : make_double2(0.0, 0.0);
+        }
+      }
+      for (int step = 0; step < b; ++step) {
+        int a1 = warp + step;
+        if (a1 >= b) a1 -= b;
+        const bool active = mine && J * b + a1 < nrows;
+        rot |= rotate_reg<E>(x, smem + (b + a1) * mt, active, p.m, mt, p.tol, floor2, lane);
+        __syncthreads();
+      }
+      if (mine) {   // write row q of block I back from the registers
+        double2* dst = Y + (long long)(I * b + warp) * p.ld;
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+          const int k = lane + 32 * e;
+          if (k < mt) dst[k] = x[e];
+        }
+      }
+      for (int v = warp; v < b; v += nwarps) {   // block J from shared memory
+        const int row = J * b + v;
+        if (row < nrows) {
+          double2* dst = Y + (long long)row * p.ld;
+          const double2* src = smem + (b + v) * mt;
+          for (int k = lane; k < mt; k += 32) dst[k] = src[k];
+        }
+      }
+      if (rot && lane == 0) atomicAdd(&cnt[sw], 1);
+      matrix_barrier(bar, ncta, phase, errflag);
+    }
+    if (*((volatile int*)&cnt[sw]) == 0 || *((volatile int*)errflag)) break;
+  }
+}
+
 // max over rows of |row[0..m)|^2, stored as a double after the 32 sweep counters of each batch entry
 __global__ void __launch_bounds__(256) row_norm_max_kernel(int n, int m, int ld, long long batchStride,
                                                            const double2* __restrict__ Yall, int* __restrict__ work) {
@@ -480,6 +626,8 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
                                      smemMax - 1024));
       MPDO_CUDA(cudaFuncSetAttribute(jacobi_persistent_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      smemMax - 1024));
+      MPDO_CUDA(cudaFuncSetAttribute(jacobi_persistent_reg_kernel<16, 512>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024));
       if (getenv("MPDO_JACOBI_MULTILAUNCH")) coop = 0;   // debugging knob
     }
     const long long ctas = (long long)(nbp / 2) * batch;
@@ -487,7 +635,16 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
       TimedLaunch timed(1, 0.0, 0.0, st);
       void* args[] = {(void*)&a, (void*)&Y};
       const void* fn = G == 32 ? (const void*)jacobi_persistent_kernel<32> : (const void*)jacobi_persistent_kernel<16>;
-      cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(nbp / 2, batch), dim3(threads), args, smem, st);
+      unsigned nthreads = threads;
+      static const bool noReg = getenv("MPDO_JACOBI_NOREG") != nullptr;   // debugging knob
+      if (!noReg && mt > 256 && mt <= 512 && b <= 16) {
+        // rows of 257..512 entries: one warp per row, rows of block I register-resident (see rotate_reg). Measured
+        // on B200: 18% faster at mt = 512; no gain at mt = 256 (8 entries per lane) and 40% slower at mt = 1024
+        // (32 entries per lane leave 7 warps per SM), so those keep the shared-memory kernel.
+        fn = (const void*)jacobi_persistent_reg_kernel<16, 512>;
+        nthreads = 32u * (unsigned)b;
+      }
+      cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(nbp / 2, batch), dim3(nthreads), args, smem, st);
       if (e == cudaSuccess) {
         ++g_launches;
         return 0;
