@@ -77,18 +77,18 @@ __device__ __forceinline__ long long map_idx(const mpdo_idxmap& m, int i) {
 __device__ __forceinline__ void matrix_barrier(unsigned* bar, unsigned nblk, unsigned& phase, int* errflag) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(bar, 1u);
+    // arrive: release at gpu scope (cumulative over the CTA's writes ordered by the bar.sync above), no return value
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
     const unsigned target = (phase + 1u) * nblk;
-    unsigned spins = 0;
-    while (*((volatile unsigned*)bar) < target) {
-      __nanosleep(40);
-      if (++spins > (1u << 26)) {  // ~seconds: never expected; refuse to hang the device
+    unsigned spins = 0, seen;
+    for (;;) {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+      if (seen >= target) break;
+      if (++spins > (1u << 24)) {  // ~seconds: never expected; refuse to hang the device
         *errflag = 1;
         break;
       }
     }
-    __threadfence();
   }
   __syncthreads();
   ++phase;

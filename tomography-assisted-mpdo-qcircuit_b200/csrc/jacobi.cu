@@ -428,27 +428,22 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_reg_kernel(JacobiArgs 
 // max over rows of |row[0..m)|^2, stored as a double after the 32 sweep counters of each batch entry
 __global__ void __launch_bounds__(256) row_norm_max_kernel(int n, int m, int ld, long long batchStride,
                                                            const double2* __restrict__ Yall, int* __restrict__ work) {
-  __shared__ double wmax[8];
-  const int bidx = blockIdx.x;
-  const double2* Y = Yall + (long long)bidx * batchStride;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  double best = 0;
-  for (int r = warp; r < n; r += nw) {
-    const double2* row = Y + (long long)r * ld;
-    double a = 0;
-    for (int k = lane; k < m; k += 32) {
-      double2 u = row[k];
-      a = fma(u.x, u.x, fma(u.y, u.y, a));
-    }
-    a = warp_sum(a);
-    best = fmax(best, a);
+  // one warp per row; non-negative doubles order like their bit patterns, so the maximum is one 64-bit atomicMax
+  // (the slot was zeroed with the rest of `work`)
+  const int bidx = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= n) return;
+  const double2* row = Yall + (long long)bidx * batchStride + (long long)r * ld;
+  double a = 0;
+  for (int k = lane; k < m; k += 32) {
+    double2 u = row[k];
+    a = fma(u.x, u.x, fma(u.y, u.y, a));
   }
-  if (lane == 0) wmax[warp] = best;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < nw; ++w) best = fmax(best, wmax[w]);
-    *reinterpret_cast<double*>(work + (long long)bidx * WORK_INTS + 32) = best;
-  }
+  a = warp_sum(a);
+  if (lane == 0 && a > 0)
+    atomicMax(reinterpret_cast<unsigned long long*>(work + (long long)bidx * WORK_INTS + 32),
+              (unsigned long long)__double_as_longlong(a));
 }
 
 // ---- finalize: norms, descending sort, optional normalised rows / accumulator ------------------
@@ -473,19 +468,26 @@ __global__ void __launch_bounds__(256) rows_finalize_kernel(int n, int m, int mz
     if (lane == 0) norms[r] = sqrt(a);
   }
   __syncthreads();
-  for (int r = threadIdx.x; r < n; r += blockDim.x) {
-    double v = norms[r];
+  // rank of every row in the descending order (ties: lower row first): one warp per row counts in parallel
+  for (int r = warp; r < n; r += nw) {
+    const double v = norms[r];
     int rk = 0;
-    for (int q = 0; q < n; ++q) {
-      double w = norms[q];
+    for (int q = lane; q < n; q += 32) {
+      const double w = norms[q];
       rk += (w > v) || (w == v && q < r);
     }
-    rank[r] = rk;
-    sOut[(long long)bidx * n + rk] = (normalize & 2) ? v * v : v;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
+    if (lane == 0) {
+      rank[r] = rk;
+      sOut[(long long)bidx * n + rk] = (normalize & 2) ? v * v : v;
+    }
   }
   __syncthreads();
   double vmax = 0;
-  for (int q = 0; q < n; ++q) vmax = fmax(vmax, norms[q]);
+  for (int q = lane; q < n; q += 32) vmax = fmax(vmax, norms[q]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
   for (int r = warp; r < n; r += nw) {
     const double2* row = Y + (long long)r * ld;
     const int rk = rank[r];
@@ -505,6 +507,85 @@ __global__ void __launch_bounds__(256) rows_finalize_kernel(int n, int m, int mz
       double2* dst = Z + ((long long)bidx * n + rk) * mz;
       for (int k = lane; k < mz; k += 32) dst[k] = row[m + k];
     }
+  }
+}
+
+// ---- finalize for large matrices: the same result from three gridded kernels (a single CTA walking a 1024 x 1024
+// matrix twice was 0.5 ms on the critical path of every decomposition) ------------------------------------------
+__global__ void __launch_bounds__(256) row_norms_kernel(int n, int m, int ld, long long batchStride,
+                                                        const double2* __restrict__ Yall, double* __restrict__ sOut) {
+  const int bidx = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= n) return;
+  const double2* row = Yall + (long long)bidx * batchStride + (long long)r * ld;
+  double a = 0;
+  for (int k = lane; k < m; k += 32) {
+    const double2 u = row[k];
+    a = fma(u.x, u.x, fma(u.y, u.y, a));
+  }
+  a = warp_sum(a);
+  if (lane == 0) sOut[(long long)bidx * n + r] = sqrt(a);   // unsorted for now
+}
+
+__global__ void __launch_bounds__(256) rows_scatter_kernel(int n, int m, int mz, int ld, long long batchStride,
+                                                           const double2* __restrict__ Yall,
+                                                           const double* __restrict__ normsIn, double2* __restrict__ Yn,
+                                                           double2* __restrict__ Z, int normalize, double zeroTol) {
+  extern __shared__ double fsm[];  // norms[n]
+  const int bidx = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int q = threadIdx.x; q < n; q += blockDim.x) fsm[q] = normsIn[(long long)bidx * n + q];
+  __syncthreads();
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= n) return;
+  const double v = fsm[r];
+  int rk = 0;
+  double vmax = 0;
+  for (int q = lane; q < n; q += 32) {
+    const double w = fsm[q];
+    rk += (w > v) || (w == v && q < r);
+    vmax = fmax(vmax, w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rk += __shfl_xor_sync(0xffffffffu, rk, o);
+    vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  }
+  const double2* row = Yall + (long long)bidx * batchStride + (long long)r * ld;
+  if (Yn) {
+    double sc = 1.0;
+    if (normalize & 1) sc = (v > zeroTol * vmax && v > 0) ? 1.0 / v : 0.0;
+    double2* dst = Yn + ((long long)bidx * n + rk) * m;
+    for (int k = lane; k < m; k += 32) {
+      double2 u = row[k];
+      u.x *= sc;
+      u.y *= sc;
+      dst[k] = u;
+    }
+  }
+  if (Z) {
+    double2* dst = Z + ((long long)bidx * n + rk) * mz;
+    for (int k = lane; k < mz; k += 32) dst[k] = row[m + k];
+  }
+}
+
+__global__ void __launch_bounds__(256) sort_norms_kernel(int n, double* __restrict__ s, int squared) {
+  extern __shared__ double fsm[];
+  const int bidx = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int q = threadIdx.x; q < n; q += blockDim.x) fsm[q] = s[(long long)bidx * n + q];
+  __syncthreads();
+  for (int r = warp; r < n; r += nw) {
+    const double v = fsm[r];
+    int rk = 0;
+    for (int q = lane; q < n; q += 32) {
+      const double w = fsm[q];
+      rk += (w > v) || (w == v && q < r);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rk += __shfl_xor_sync(0xffffffffu, rk, o);
+    if (lane == 0) s[(long long)bidx * n + rk] = squared ? v * v : v;
   }
 }
 
@@ -544,7 +625,7 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
   static const bool trace = getenv("MPDO_TRACE") != nullptr;
   if (trace) fprintf(stderr, "[mpdo] jacobi n=%d m=%d mt=%d batch=%d\n", n, m, mt, batch);
   if (batch > 65535) return fail(MPDO_EINVAL, "mpdo_jacobi_rows: batch > 65535");
-  row_norm_max_kernel<<<batch, 256, 0, st>>>(n, m, ld, batchStride, (const double2*)Y, work);
+  row_norm_max_kernel<<<dim3((n + 7) / 8, batch), 256, 0, st>>>(n, m, ld, batchStride, (const double2*)Y, work);
   {
     int rc = check_launch("row_norm_max_kernel");
     if (rc) return rc;
@@ -692,6 +773,21 @@ extern "C" int mpdo_rows_finalize(int batch, int n, int m, int mz, int ld, int64
   if (!Y || !s || m <= 0) return fail(MPDO_EINVAL, "mpdo_rows_finalize: bad argument");
   const size_t smem = (size_t)n * (sizeof(double) + sizeof(int));
   if (smem > 48 * 1024) return fail(MPDO_ENOSMEM, "mpdo_rows_finalize: n too large");
+  if (n >= 192 && batch <= 4096) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid((n + 7) / 8, batch);
+    row_norms_kernel<<<grid, 256, 0, st>>>(n, m, ld, batchStride, (const double2*)Y, s);
+    int rc = check_launch("row_norms_kernel");
+    if (rc) return rc;
+    if (Yn || Z) {
+      rows_scatter_kernel<<<grid, 256, sizeof(double) * (size_t)n, st>>>(n, m, mz, ld, batchStride, (const double2*)Y, s,
+                                                                        (double2*)Yn, (double2*)Z, normalize, zeroTol);
+      rc = check_launch("rows_scatter_kernel");
+      if (rc) return rc;
+    }
+    sort_norms_kernel<<<batch, 256, sizeof(double) * (size_t)n, st>>>(n, s, (normalize & 2) ? 1 : 0);
+    return check_launch("sort_norms_kernel");
+  }
   rows_finalize_kernel<<<batch, 256, smem, (cudaStream_t)stream>>>(n, m, mz, ld, batchStride, (const double2*)Y, s,
                                                                   (double2*)Yn, (double2*)Z, normalize, zeroTol);
   return check_launch("rows_finalize_kernel");
