@@ -191,6 +191,11 @@ int mpdo_timing_enable(int on);
 int mpdo_timing_summary(int cls, double minFlops, double* seconds, double* flops, double* bytes, int64_t* launches,
                         double* maxFlopsSeconds, double* maxFlops);
 
+/* Hands the scratch memory cached by the step-level entry points (one stream-ordered pool per calling thread) back
+ * to the driver. The step functions return cudaErrorMemoryAllocation (2) only after trying this themselves; a caller
+ * that shares the device with another caching allocator (torch) releases that cache and retries. */
+int mpdo_trim_pools(void);
+
 /* Library / device information. */
 int mpdo_version(void);
 const char* mpdo_last_error(void);

@@ -57,6 +57,7 @@ SYMBOLS = {
     'mpdo_split_2q': (C.c_int, [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                                C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     'mpdo_cast': (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mpdo_trim_pools': (C.c_int, []),
     'mpdo_timing_enable': (C.c_int, [C.c_int]),
     'mpdo_timing_summary': (C.c_int, [C.c_int, C.c_double] + [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_int64)] +
                             [C.POINTER(C.c_double)] * 2),

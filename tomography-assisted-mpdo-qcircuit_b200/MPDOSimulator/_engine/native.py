@@ -22,19 +22,34 @@ def _p(t):
     return C.c_void_p(t.data_ptr())
 
 
+_CUDA_OOM = 2   # cudaErrorMemoryAllocation
+
+
 class NativeEngine(Engine):
     def __init__(self, prims, dtype, npass=None):
         super().__init__(prims, dtype, npass)
         self.lib = _lib.load()
         self.dt = _DT[dtype]
 
+    def _call(self, what, fn, *args):
+        """One library call; on device-memory exhaustion (the library has already trimmed its own pools) give torch's
+        cached blocks back to the driver and retry once. The step functions write nothing the caller keeps before
+        their scratch is allocated, so a retry is safe."""
+        rc = fn(*args)
+        if rc == _CUDA_OOM:
+            torch.cuda.synchronize()
+            torch.cuda.empty_cache()
+            self.lib.mpdo_trim_pools()
+            rc = fn(*args)
+        _lib.check(rc, what)
+
     def qr_step(self, Ti, Tn):
         Ti, Tn = Ti.contiguous(), Tn.contiguous()
         Bn, l, _, a, r = Ti.shape
         _, _, _, a2, r2 = Tn.shape
         Q, Tn_new = torch.empty_like(Ti), torch.empty_like(Tn)
-        _lib.check(self.lib.mpdo_qr_step(self.dt, self.npass, Bn, l, a, r, _p(Ti), a2, r2, _p(Tn), _p(Q), _p(Tn_new),
-                                         _stream()), 'mpdo_qr_step')
+        self._call('mpdo_qr_step', self.lib.mpdo_qr_step, self.dt, self.npass, Bn, l, a, r, _p(Ti), a2, r2, _p(Tn), _p(Q),
+                   _p(Tn_new), _stream())
         return Q, Tn_new
 
     def bond_svd_step(self, Tl, Tr, chi, max_err=None):
@@ -47,8 +62,8 @@ class NativeEngine(Engine):
         Tl_n = torch.empty((Bn, lp, 2, ap, k), dtype=Tl.dtype, device=Tl.device)
         Tr_n = torch.empty((Bn, k, 2, a, r), dtype=Tr.dtype, device=Tr.device)
         sv = torch.empty((Bn, l), dtype=torch.float64, device=Tr.device)
-        _lib.check(self.lib.mpdo_bond_svd_step(self.dt, self.npass, Bn, lp, ap, l, _p(Tl), a, r, _p(Tr), k, _p(Tl_n),
-                                               _p(Tr_n), _p(sv), _stream()), 'mpdo_bond_svd_step')
+        self._call('mpdo_bond_svd_step', self.lib.mpdo_bond_svd_step, self.dt, self.npass, Bn, lp, ap, l, _p(Tl), a, r,
+                   _p(Tr), k, _p(Tl_n), _p(Tr_n), _p(sv), _stream())
         disc = sv[:, k:].clamp_min(0).sqrt() if self.npass == 1 else sv[:, k:]
         return Tl_n, Tr_n, disc
 
@@ -60,8 +75,8 @@ class NativeEngine(Engine):
         k = min(int(kappa), a)
         T_n = torch.empty((Bn, l, 2, k, r), dtype=T.dtype, device=T.device)
         disc = torch.empty((Bn,), dtype=torch.float64, device=T.device)
-        _lib.check(self.lib.mpdo_kappa_truncate(self.dt, Bn, l, a, r, _p(T), k, _p(T_n), _p(disc), _stream()),
-                   'mpdo_kappa_truncate')
+        self._call('mpdo_kappa_truncate', self.lib.mpdo_kappa_truncate, self.dt, Bn, l, a, r, _p(T), k, _p(T_n),
+                   _p(disc), _stream())
         return T_n, disc.unsqueeze(1)
 
     def split_2q(self, Tlo, Thi, G, max_err=2.718281828459045e-8):
@@ -79,10 +94,9 @@ class NativeEngine(Engine):
 
         cb = ALLOC_FN(alloc)
         k = C.c_int(0)
-        _lib.check(self.lib.mpdo_split_2q(self.dt, self.npass, Bn, l, a0, m, _p(Tlo), a1, r, _p(Thi), Bg, K, _p(G),
-                                          -1.0 if max_err is None else float(max_err), C.cast(cb, C.c_void_p), None,
-                                          C.byref(k),
-                                          _stream()), 'mpdo_split_2q')
+        self._call('mpdo_split_2q', self.lib.mpdo_split_2q, self.dt, self.npass, Bn, l, a0, m, _p(Tlo), a1, r, _p(Thi),
+                   Bg, K, _p(G), -1.0 if max_err is None else float(max_err), C.cast(cb, C.c_void_p), None,
+                   C.byref(k), _stream())
         kk = k.value
         self.stats['last_rank'] = kk
         return outs[0].view(Bn, l, 2, a0, kk), outs[1].view(Bn, kk, 2, K * a1, r)

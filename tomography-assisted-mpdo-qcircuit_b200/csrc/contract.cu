@@ -21,7 +21,7 @@ constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
 constexpr int TM = BM / 16, TN = BN / 16;
 
 template <typename TA, typename TB, typename TC, typename R>
-__global__ void __launch_bounds__(NT) contract_kernel(const mpdo_contract_desc d, const TA* __restrict__ A,
+__global__ void __launch_bounds__(NT, 2) contract_kernel(const mpdo_contract_desc d, const TA* __restrict__ A,
                                                       const TB* __restrict__ B, TC* __restrict__ C, int tilesM,
                                                       int tilesN, int kChunk) {
   using CR = typename cplx<R>::type;
@@ -82,16 +82,17 @@ __global__ void __launch_bounds__(NT) contract_kernel(const mpdo_contract_desc d
     offBj[r] = (j < d.N) ? map_idx(d.Bj, j) : -1;
   }
 
-  CR ra[LA], rb[LB];
+  TA ra[LA];   // prefetched in the operand's own type (half the registers for fp32 operands under fp64 accumulate)
+  TB rb[LB];
   auto load_tile = [&](int k0) {
 #pragma unroll
     for (int r = 0; r < LA; ++r) {
       int k = k0 + (akf ? a_kk : a_kk + r * (NT / BM));
-      CR v;
+      TA v;
       v.x = 0;
       v.y = 0;
       if (k < kEnd && offAi[r] >= 0) {
-        v = cconv<CR>(Ab[offAi[r] + map_idx(d.Ak, k)]);
+        v = Ab[offAi[r] + map_idx(d.Ak, k)];
         if (d.conjA) v.y = -v.y;
       }
       ra[r] = v;
@@ -99,11 +100,11 @@ __global__ void __launch_bounds__(NT) contract_kernel(const mpdo_contract_desc d
 #pragma unroll
     for (int r = 0; r < LB; ++r) {
       int k = k0 + (bjf ? b_kk + r * (NT / BN) : b_kk);
-      CR v;
+      TB v;
       v.x = 0;
       v.y = 0;
       if (k < kEnd && offBj[r] >= 0) {
-        v = cconv<CR>(Bb[offBj[r] + map_idx(d.Bk, k)]);
+        v = Bb[offBj[r] + map_idx(d.Bk, k)];
         if (d.conjB) v.y = -v.y;
       }
       rb[r] = v;
@@ -113,16 +114,16 @@ __global__ void __launch_bounds__(NT) contract_kernel(const mpdo_contract_desc d
 #pragma unroll
     for (int r = 0; r < LA; ++r) {
       if (akf)
-        As[a_kk][a_ii + r * (NT / BK)] = ra[r];
+        As[a_kk][a_ii + r * (NT / BK)] = cconv<CR>(ra[r]);
       else
-        As[a_kk + r * (NT / BM)][a_ii] = ra[r];
+        As[a_kk + r * (NT / BM)][a_ii] = cconv<CR>(ra[r]);
     }
 #pragma unroll
     for (int r = 0; r < LB; ++r) {
       if (bjf)
-        Bs[b_kk + r * (NT / BN)][b_jj] = rb[r];
+        Bs[b_kk + r * (NT / BN)][b_jj] = cconv<CR>(rb[r]);
       else
-        Bs[b_kk][b_jj + r * (NT / BK)] = rb[r];
+        Bs[b_kk][b_jj + r * (NT / BK)] = cconv<CR>(rb[r]);
     }
   };
 

@@ -41,6 +41,19 @@ static int collapse(const Tn& t, int d0, int cnt, Level* lv) {
   return k;
 }
 
+std::mutex& pool_registry_mutex() {
+  static std::mutex mu;
+  return mu;
+}
+std::vector<cudaMemPool_t>& pool_registry() {
+  static std::vector<cudaMemPool_t> pools;
+  return pools;
+}
+void trim_all_pools() {
+  std::lock_guard<std::mutex> lk(pool_registry_mutex());
+  for (cudaMemPool_t p : pool_registry()) cudaMemPoolTrimTo(p, 0);
+}
+
 static bool to_map(const Level* lv, int k, mpdo_idxmap* m) {
   memset(m, 0, sizeof(*m));
   if (k == 0) return true;
@@ -581,6 +594,11 @@ using namespace mpdo::eng;
 // ===================================================================================================
 // C entry points
 // ===================================================================================================
+
+extern "C" int mpdo_trim_pools(void) {
+  trim_all_pools();
+  return 0;
+}
 
 extern "C" int mpdo_qr_step(int dtype, int npass, int B, int l, int a, int r, const void* Ti, int a2, int r2,
                             const void* Tn_in, void* Q_out, void* Tn_out, void* stream) {

@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include <initializer_list>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -79,6 +80,11 @@ struct Roles {
   int nb, n1, n2;
 };
 
+// every per-thread scratch pool, so that an allocation failure in one strand can take back what the others cache
+std::mutex& pool_registry_mutex();
+std::vector<cudaMemPool_t>& pool_registry();
+void trim_all_pools();
+
 struct Arena {  // scratch buffers freed (stream-ordered) when the step returns
   cudaStream_t st;
   std::vector<void*> bufs;
@@ -100,8 +106,10 @@ struct Arena {  // scratch buffers freed (stream-ordered) when the step returns
       props.location.type = cudaMemLocationTypeDevice;
       props.location.id = dev;
       if (cudaMemPoolCreate(&tpool, &props) == cudaSuccess) {
-        unsigned long long keep = ~0ULL;
+        unsigned long long keep = 4ULL << 30;   // cache up to 4 GiB of freed scratch per strand thread
         cudaMemPoolSetAttribute(tpool, cudaMemPoolAttrReleaseThreshold, &keep);
+        std::lock_guard<std::mutex> lk(pool_registry_mutex());
+        pool_registry().push_back(tpool);
       } else {
         tpool = nullptr;
         cudaGetLastError();
@@ -116,7 +124,14 @@ struct Arena {  // scratch buffers freed (stream-ordered) when the step returns
     void* ptr = nullptr;
     if (bytes == 0) bytes = 16;
     cudaError_t e = pool ? cudaMallocFromPoolAsync(&ptr, bytes, pool, st) : cudaMallocAsync(&ptr, bytes, st);
+    if (e == cudaErrorMemoryAllocation) {   // take back what the other strands' pools cache, then retry once
+      cudaGetLastError();
+      cudaStreamSynchronize(st);
+      trim_all_pools();
+      e = pool ? cudaMallocFromPoolAsync(&ptr, bytes, pool, st) : cudaMallocAsync(&ptr, bytes, st);
+    }
     if (e != cudaSuccess) {
+      cudaGetLastError();
       snprintf(g_err, sizeof(g_err), "cudaMallocAsync(%zu): %s", bytes, cudaGetErrorString(e));
       err = (int)e;
       return nullptr;
