@@ -41,6 +41,11 @@ class Engine:
     def _empty(self, shape, like, dtype=None):
         return torch.empty(shape, dtype=dtype or self.dtype, device=like.device)
 
+    def _rr(self, G):
+        """Preconditioned (rank-revealing) eigen-solver: complex64 states only, and not for large batches, which
+        already fill the GPU with the classic batched Jacobi (same policy as csrc/engine.cu Ctx::set_batch)."""
+        return self.npass == 1 and G.shape[0] < 32
+
     def _gram_cols(self, X, roles):
         """G[b,c,c'] = sum_rows conj(X[b,rows,c]) X[b,rows,c'] for a view X [b | rows | cols]."""
         nb, nr, nc = roles
@@ -77,7 +82,7 @@ class Engine:
         p = self.p
         nb, nr, nc = roles
         G = self._gram_cols(X, roles)
-        lam, Vh = p.eigh_psd(G, self.jacobi_tol, rank_revealing=self.npass == 1)
+        lam, Vh = p.eigh_psd(G, self.jacobi_tol, rank_revealing=self._rr(G))
         n = G.shape[1]
         if self.npass == 1:
             Xs = p.rowscale(Vh, lam, n, -0.5, self.null_tol, 0, C128)
@@ -101,7 +106,7 @@ class Engine:
         p = self.p
         nb, nr, nc = roles
         G = self._gram_rows(M, roles)
-        lam, Uh = p.eigh_psd(G, self.jacobi_tol, rank_revealing=self.npass == 1)
+        lam, Uh = p.eigh_psd(G, self.jacobi_tol, rank_revealing=self._rr(G))
         n = G.shape[1]
         if self.npass == 1:
             F = p.rowscale(Uh, lam, n, -0.5, self.null_tol, 0, C128)
@@ -133,7 +138,7 @@ class Engine:
         p = self.p
         if self.npass == 1:
             G = self._gram_rows(M, roles)
-            lam, Uh = p.eigh_psd(G, self.jacobi_tol, rank_revealing=self.npass == 1)
+            lam, Uh = p.eigh_psd(G, self.jacobi_tol, rank_revealing=self._rr(G))
             right = lambda k, dt: p.rowscale(Uh, lam, k, -0.25, self.null_tol, 0, dt)
             left = lambda k, dt: p.rowscale(Uh, lam, k, 0.25, self.null_tol, 0, dt)
             return M, lam, True, right, left
@@ -322,7 +327,7 @@ class Engine:
         for it in range(max_iter):
             # orthonormalise the rows of Zr
             H = self._gram_rows(Zr, (1, 1, 1))
-            lam, Uh = p.eigh_psd(H, self.jacobi_tol, rank_revealing=self.npass == 1)
+            lam, Uh = p.eigh_psd(H, self.jacobi_tol, rank_revealing=self._rr(H))
             Yr = torch.empty((Bn, blk, n), dtype=C128, device=G.device)
             p.contract(p.rowscale(Uh, lam, blk, -0.5, self.null_tol, 0, C128), (1, 1, 1), Zr, (1, 1, 1), Yr, (1, 1, 1))
             Zr = torch.empty((Bn, blk, n), dtype=C128, device=G.device)
@@ -330,7 +335,7 @@ class Engine:
             # Rayleigh-Ritz in the block: Bm = Zr Yr^h (Hermitian PSD), rotate both to the Ritz basis
             Bm = torch.empty((Bn, blk, blk), dtype=C128, device=G.device)
             p.contract(Zr, (1, 1, 1), Yr.permute(0, 2, 1), (1, 1, 1), Bm, (1, 1, 1), conjB=True)
-            theta, Wh = p.eigh_psd(Bm, self.jacobi_tol, rank_revealing=self.npass == 1)
+            theta, Wh = p.eigh_psd(Bm, self.jacobi_tol, rank_revealing=self._rr(Bm))
             Yn = torch.empty_like(Yr)
             Zn = torch.empty_like(Zr)
             p.contract(Wh, (1, 1, 1), Yr, (1, 1, 1), Yn, (1, 1, 1))
@@ -368,7 +373,7 @@ class Engine:
                 p.contract(Vt.to(self.dtype), (1, 1, 1), T.permute(0, 3, 1, 2, 4), (1, 1, 3),
                            T_n.permute(0, 3, 1, 2, 4), (1, 1, 3))
                 return T_n, disc
-        lam, Vh = p.eigh_psd(G, self.jacobi_tol, rank_revealing=self.npass == 1)
+        lam, Vh = p.eigh_psd(G, self.jacobi_tol, rank_revealing=self._rr(G))
         k = self._keep(lam, kappa, max_err, True, squared=True)
         disc = lam[:, k:].clamp_min(0).sqrt()
         # T'[l,s,j,r] = sum_a conj(Vh[j,a]) T[l,s,a,r]

@@ -80,9 +80,13 @@ struct Roles {
   int nb, n1, n2;
 };
 
-// every per-thread scratch pool, so that an allocation failure in one strand can take back what the others cache
-std::mutex& pool_registry_mutex();
-std::vector<cudaMemPool_t>& pool_registry();
+// One stream-ordered scratch pool per device, shared by every calling thread. Strands run on different streams from
+// different threads; with the driver's default pool a buffer freed on one stream and reused on another makes the
+// second stream wait for the first (the allocator orders the reuse after the free), which serialises the strands.
+// This pool forbids that kind of reuse (cudaMemPoolReuseAllowInternalDependencies = 0): a freed block goes to another
+// stream only once the work before its free has completed (opportunistic reuse), otherwise the pool grows. Freed
+// scratch stays cached (release threshold = max) until mpdo_trim_pools() or an allocation failure trims it.
+cudaMemPool_t scratch_pool();
 void trim_all_pools();
 
 struct Arena {  // scratch buffers freed (stream-ordered) when the step returns
@@ -90,33 +94,7 @@ struct Arena {  // scratch buffers freed (stream-ordered) when the step returns
   std::vector<void*> bufs;
   int err = 0;
   cudaMemPool_t pool = nullptr;
-  explicit Arena(cudaStream_t s) : st(s) {
-    // One private pool per host thread. Strands run on different streams from different threads; with the shared
-    // default pool a buffer freed on one stream and reused on another makes the second stream wait for the first
-    // (the allocator orders the reuse after the free), which serialises the strands. The release threshold keeps
-    // freed scratch cached instead of handing it back to the OS at every synchronisation.
-    static thread_local cudaMemPool_t tpool = nullptr;
-    if (!tpool) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaMemPoolProps props;
-      memset(&props, 0, sizeof(props));
-      props.allocType = cudaMemAllocationTypePinned;
-      props.handleTypes = cudaMemHandleTypeNone;
-      props.location.type = cudaMemLocationTypeDevice;
-      props.location.id = dev;
-      if (cudaMemPoolCreate(&tpool, &props) == cudaSuccess) {
-        unsigned long long keep = 4ULL << 30;   // cache up to 4 GiB of freed scratch per strand thread
-        cudaMemPoolSetAttribute(tpool, cudaMemPoolAttrReleaseThreshold, &keep);
-        std::lock_guard<std::mutex> lk(pool_registry_mutex());
-        pool_registry().push_back(tpool);
-      } else {
-        tpool = nullptr;
-        cudaGetLastError();
-      }
-    }
-    pool = tpool;
-  }
+  explicit Arena(cudaStream_t s) : st(s), pool(scratch_pool()) {}
   ~Arena() {
     for (void* b : bufs) cudaFreeAsync(b, st);
   }

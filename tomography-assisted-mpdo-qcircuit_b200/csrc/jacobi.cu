@@ -220,62 +220,79 @@ __global__ void __launch_bounds__(1024) jacobi_persistent_kernel(JacobiArgs p, d
   if (nrows < 2) return;   // uniform over the CTAs of this matrix: nobody reaches a barrier
   // only the blocks that hold non-zero rows take part in the tournament
   const int nbp = (((nrows + b - 1) / b) + 1) & ~1;
-  const unsigned ncta = (unsigned)(nbp / 2);
+  // gridDim.x CTAs share the nbp/2 block pairs of a round (one each when the matrix has the GPU to itself, all of
+  // them in one CTA when the batch fills the GPU: then there is no device-wide barrier at all)
+  const unsigned ncta = min((unsigned)(nbp / 2), gridDim.x);
   if (blockIdx.x >= ncta) return;
   const int be = (b + 1) & ~1;
   const int half = be / 2;
 
   for (int sw = 0; sw < p.maxSweeps; ++sw) {
+    int rotSweep = 0;
     for (int round = 0; round < nbp - 1; ++round) {
-      int I, J;
-      rr_pair(nbp, round, blockIdx.x, I, J);
-      for (int v = warp; v < 2 * b; v += nwarps) {  // stage (L2 reads: other SMs wrote these rows last round)
-        const int row = (v < b) ? I * b + v : J * b + (v - b);
-        double2* dst = smem + v * mt;
-        if (row < nrows) {
-          const double2* src = Y + (long long)row * p.ld;
-          for (int k = lane; k < mt; k += 32) dst[k] = __ldcg(src + k);
-        }
-      }
-      __syncthreads();
       int rot = 0;
-      if (round == 0) {
-        for (int step = 0; step < be - 1; ++step) {
-          for (int base = 0; base < be; base += nslots) {
+      for (int pairIdx = blockIdx.x; pairIdx < nbp / 2; pairIdx += ncta) {
+        int I, J;
+        rr_pair(nbp, round, pairIdx, I, J);
+        for (int v = warp; v < 2 * b; v += nwarps) {  // stage (L2 reads: other SMs wrote these rows last round)
+          const int row = (v < b) ? I * b + v : J * b + (v - b);
+          double2* dst = smem + v * mt;
+          if (row < nrows) {
+            const double2* src = Y + (long long)row * p.ld;
+            for (int k = lane; k < mt; k += 32) dst[k] = __ldcg(src + k);
+          }
+        }
+        __syncthreads();
+        if (round == 0) {
+          for (int step = 0; step < be - 1; ++step) {
+            for (int base = 0; base < be; base += nslots) {
+              const int q = base + slot;
+              const int blk = q >= half ? 1 : 0;
+              int a0, a1;
+              rr_pair(be, step, q - blk * half, a0, a1);
+              const int first = (blk ? J : I) * b;
+              const bool active = q < be && a0 < b && a1 < b && first + a0 < nrows && first + a1 < nrows;
+              rot |= rotate_pair<G>(smem + (blk * b + a0) * mt, smem + (blk * b + a1) * mt, active, p.m, mt, p.tol,
+                                    floor2, sub);
+            }
+            __syncthreads();
+          }
+        }
+        for (int step = 0; step < b; ++step) {
+          for (int base = 0; base < b; base += nslots) {
             const int q = base + slot;
-            const int blk = q >= half ? 1 : 0;
-            int a0, a1;
-            rr_pair(be, step, q - blk * half, a0, a1);
-            const int first = (blk ? J : I) * b;
-            const bool active = q < be && a0 < b && a1 < b && first + a0 < nrows && first + a1 < nrows;
-            rot |= rotate_pair<G>(smem + (blk * b + a0) * mt, smem + (blk * b + a1) * mt, active, p.m, mt, p.tol,
-                                  floor2, sub);
+            int a1 = q + step;
+            if (a1 >= b) a1 -= b;
+            const bool active = q < b && I * b + q < nrows && J * b + a1 < nrows;
+            rot |= rotate_pair<G>(smem + q * mt, smem + (b + a1) * mt, active, p.m, mt, p.tol, floor2, sub);
           }
           __syncthreads();
         }
-      }
-      for (int step = 0; step < b; ++step) {
-        for (int base = 0; base < b; base += nslots) {
-          const int q = base + slot;
-          int a1 = q + step;
-          if (a1 >= b) a1 -= b;
-          const bool active = q < b && I * b + q < nrows && J * b + a1 < nrows;
-          rot |= rotate_pair<G>(smem + q * mt, smem + (b + a1) * mt, active, p.m, mt, p.tol, floor2, sub);
+        for (int v = warp; v < 2 * b; v += nwarps) {  // write back
+          const int row = (v < b) ? I * b + v : J * b + (v - b);
+          if (row < nrows) {
+            double2* dst = Y + (long long)row * p.ld;
+            const double2* src = smem + v * mt;
+            for (int k = lane; k < mt; k += 32) dst[k] = src[k];
+          }
         }
-        __syncthreads();
+        __syncthreads();   // the staging area is reused by the next pair of this CTA
       }
-      for (int v = warp; v < 2 * b; v += nwarps) {  // write back
-        const int row = (v < b) ? I * b + v : J * b + (v - b);
-        if (row < nrows) {
-          double2* dst = Y + (long long)row * p.ld;
-          const double2* src = smem + v * mt;
-          for (int k = lane; k < mt; k += 32) dst[k] = src[k];
-        }
+      if (ncta > 1) {
+        if (rot && sub == 0) atomicAdd(&cnt[sw], 1);
+        matrix_barrier(bar, ncta, phase, errflag);
+      } else {
+        rotSweep |= rot;
+        __threadfence_block();
       }
-      if (rot && sub == 0) atomicAdd(&cnt[sw], 1);
-      matrix_barrier(bar, ncta, phase, errflag);
     }
-    if (*((volatile int*)&cnt[sw]) == 0 || *((volatile int*)errflag)) break;
+    if (ncta > 1) {
+      if (*((volatile int*)&cnt[sw]) == 0 || *((volatile int*)errflag)) break;
+    } else {
+      const int any = __syncthreads_or(rotSweep);
+      if (threadIdx.x == 0) cnt[sw] = any;
+      if (!any) break;
+    }
   }
 }
 
@@ -711,21 +728,41 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024));
       if (getenv("MPDO_JACOBI_MULTILAUNCH")) coop = 0;   // debugging knob
     }
-    const long long ctas = (long long)(nbp / 2) * batch;
-    if (coop && ctas <= sms) {   // one CTA per SM (the row staging area takes most of the shared memory)
+    // CTAs per matrix: all nbp/2 block pairs of a round in parallel when the GPU has room, fewer (each CTA then
+    // walks several pairs) when the batch is large, down to one CTA per matrix, which needs no device-wide barrier
+    // and therefore no cooperative launch (any batch size).
+    const void* fn = G == 32 ? (const void*)jacobi_persistent_kernel<32> : (const void*)jacobi_persistent_kernel<16>;
+    if (G == 8) fn = nullptr;   // (tuning knob only: the 8-lane variant exists for the single-CTA kernel)
+    int perSm = 0;
+    if (fn && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, (int)threads, smem) != cudaSuccess) {
+      cudaGetLastError();
+      perSm = 0;
+    }
+    const long long capacity = (long long)perSm * sms;
+    long long P = batch > 0 ? capacity / batch : 0;
+    if (P > nbp / 2) P = nbp / 2;
+    // Measured on a 128-matrix batch of n = 512: one CTA walking all pairs of its matrix (P = 1, no barrier) takes
+    // 371 ms where the multi-launch driver below takes 206 ms, so sharing is opt-in (MPDO_JACOBI_SHARE) and the
+    // persistent kernel is used when every block pair of a round gets its own CTA.
+    static const bool share = getenv("MPDO_JACOBI_SHARE") != nullptr;
+    if (fn && perSm > 0 && coop && (P == nbp / 2 || (share && P >= 1))) {
       TimedLaunch timed(1, 0.0, 0.0, st);
       void* args[] = {(void*)&a, (void*)&Y};
-      const void* fn = G == 32 ? (const void*)jacobi_persistent_kernel<32> : (const void*)jacobi_persistent_kernel<16>;
       unsigned nthreads = threads;
       static const bool noReg = getenv("MPDO_JACOBI_NOREG") != nullptr;   // debugging knob
-      if (!noReg && mt > 256 && mt <= 512 && b <= 16) {
+      if (!noReg && P == nbp / 2 && mt > 256 && mt <= 512 && b <= 16) {
         // rows of 257..512 entries: one warp per row, rows of block I register-resident (see rotate_reg). Measured
         // on B200: 18% faster at mt = 512; no gain at mt = 256 (8 entries per lane) and 40% slower at mt = 1024
         // (32 entries per lane leave 7 warps per SM), so those keep the shared-memory kernel.
         fn = (const void*)jacobi_persistent_reg_kernel<16, 512>;
         nthreads = 32u * (unsigned)b;
       }
-      cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(nbp / 2, batch), dim3(nthreads), args, smem, st);
+      cudaError_t e;
+      if (P > 1) {
+        e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)P, batch), dim3(nthreads), args, smem, st);
+      } else {
+        e = cudaLaunchKernel(fn, dim3(1, batch), dim3(nthreads), args, smem, st);
+      }
       if (e == cudaSuccess) {
         ++g_launches;
         return 0;
