@@ -18,6 +18,8 @@ Singular-vector gauges are not unique; all comparisons with the reference use ga
 quantities. The inner index order is (new Kraus index major, old index minor) - a pure relabelling of
 an index that is only ever traced against its own conjugate.
 """
+import os
+
 import torch
 
 C128 = torch.complex128
@@ -42,9 +44,11 @@ class Engine:
         return torch.empty(shape, dtype=dtype or self.dtype, device=like.device)
 
     def _rr(self, G):
-        """Preconditioned (rank-revealing) eigen-solver: complex64 states only, and not for large batches, which
-        already fill the GPU with the classic batched Jacobi (same policy as csrc/engine.cu Ctx::set_batch)."""
-        return self.npass == 1 and G.shape[0] < 32
+        """Preconditioned (rank-revealing) eigen-solver: complex64 states only (same policy as csrc/engine.cu Ctx;
+        MPDO_BATCH_CLASSIC=1 keeps the classic batched Jacobi for batches of 32 and more)."""
+        if os.environ.get('MPDO_BATCH_CLASSIC') and G.shape[0] >= 32:
+            return False
+        return self.npass == 1
 
     def _gram_cols(self, X, roles):
         """G[b,c,c'] = sum_rows conj(X[b,rows,c]) X[b,rows,c'] for a view X [b | rows | cols]."""

@@ -13,6 +13,15 @@
 // ahead into registers; the loader picks the thread->element mapping that makes the contiguous axis of
 // each operand the fastest-varying one. complex64 operands may be accumulated in fp32 (FFMA) or fp64
 // (DFMA; B200 runs fp64 at half the fp32 rate, which is what makes fp64 Gram matrices affordable).
+//
+// fp64-accumulated contractions (Gram matrices, fp64 cores, every complex128 contraction) run on the fp64 tensor
+// pipe: the same 64x64x16 shared-memory tiles are consumed by 8 warps (4 along M x 2 along N, a 16x32 complex
+// warp tile) with mma.sync.m8n8k4.f64 (DMMA) - four real DMMAs per complex 8x8x4 block, the imaginary part of the A
+// fragment negated once in registers. One DMMA retires 256 FMAs per warp instruction where DFMA retires 32, so the
+// kernel spends its issue slots on the fp64 pipe instead of on shared-memory operand traffic. B200 retires DMMA on
+// the same fp64 units as DFMA, so the gain is small (see the dispatch in mpdo_contract for the measured numbers).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace mpdo {
@@ -20,13 +29,24 @@ namespace mpdo {
 constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
 constexpr int TM = BM / 16, TN = BN / 16;
 
-template <typename TA, typename TB, typename TC, typename R>
-__global__ void __launch_bounds__(NT, 2) contract_kernel(const mpdo_contract_desc d, const TA* __restrict__ A,
+// D(8x8) += A(8x4, row) * B(4x8, col), fp64. Fragments: A: lane holds A[lane/4][lane%4]; B: lane holds B[lane%4][lane/4];
+// C/D: lane holds C[lane/4][2*(lane%4) + {0,1}].
+__device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c[0]), "+d"(c[1])
+               : "d"(a), "d"(b));
+}
+
+template <typename TA, typename TB, typename TC, typename R, bool MMA>
+__global__ void __launch_bounds__(NT, MMA ? 1 : 2) contract_kernel(const mpdo_contract_desc d, const TA* __restrict__ A,
                                                       const TB* __restrict__ B, TC* __restrict__ C, int tilesM,
                                                       int tilesN, int kChunk) {
   using CR = typename cplx<R>::type;
-  __shared__ CR As[BK][BM + 1];
-  __shared__ CR Bs[BK][BN + 1];
+  // row stride in 16-byte units: 65 = 1 (mod 8) spreads the scalar kernel's column reads; 66 = 2 (mod 8) makes the
+  // DMMA fragment reads (4 k-rows x 2 columns per quarter warp) hit eight distinct 16-byte bank groups
+  constexpr int PAD = MMA ? 2 : 1;
+  __shared__ CR As[BK][BM + PAD];
+  __shared__ CR Bs[BK][BN + PAD];
 
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
@@ -127,94 +147,165 @@ __global__ void __launch_bounds__(NT, 2) contract_kernel(const mpdo_contract_des
     }
   };
 
-  CR acc[TM][TN];
-#pragma unroll
-  for (int u = 0; u < TM; ++u)
-#pragma unroll
-    for (int v = 0; v < TN; ++v) {
-      acc[u][v].x = 0;
-      acc[u][v].y = 0;
-    }
-
-  if (kBeg < kEnd) {
-    load_tile(kBeg);
-    store_tile();
-    __syncthreads();
-    for (int k0 = kBeg; k0 < kEnd; k0 += BK) {
-      const bool more = (k0 + BK) < kEnd;
-      if (more) load_tile(k0 + BK);
-#pragma unroll
-      for (int kk = 0; kk < BK; ++kk) {
-        CR a[TM], bb[TN];
-#pragma unroll
-        for (int u = 0; u < TM; ++u) a[u] = As[kk][ty + 16 * u];
-#pragma unroll
-        for (int v = 0; v < TN; ++v) bb[v] = Bs[kk][tx + 16 * v];
-#pragma unroll
-        for (int u = 0; u < TM; ++u)
-#pragma unroll
-          for (int v = 0; v < TN; ++v) cfma(acc[u][v], a[u], bb[v]);
-      }
-      __syncthreads();
-      if (more) {
-        store_tile();
-        __syncthreads();
-      }
-    }
-  }
-
-  // ---- epilogue --------------------------------------------------------------------------------
+  // ---- epilogue helper: one output element (alpha/beta, split-K atomics, Hermitian mirror) ------------
   using RC = typename real_of<TC>::type;
   TC* Cb = C + map_idx(d.Cb, b);
-  long long offCj[TN];
-#pragma unroll
-  for (int v = 0; v < TN; ++v) {
-    int j = j0 + tx + 16 * v;
-    offCj[v] = (j < d.N) ? map_idx(d.Cj, j) : -1;
-  }
   const R alpha = (R)d.alpha;
   const R beta = (R)d.beta;
-#pragma unroll
-  for (int u = 0; u < TM; ++u) {
-    int i = i0 + ty + 16 * u;
-    if (i >= d.M) continue;
-    long long oi = map_idx(d.Ci, i);
-#pragma unroll
-    for (int v = 0; v < TN; ++v) {
-      if (offCj[v] < 0) continue;
-      TC* p = Cb + oi + offCj[v];
-      R re = alpha * acc[u][v].x, im = alpha * acc[u][v].y;
+  auto emit = [&](int i, int j, long long oi, long long oj, R accRe, R accIm) {
+    TC* p = Cb + oi + oj;
+    R re = alpha * accRe, im = alpha * accIm;
+    if (ksplit > 1) {
+      atomicAdd(&p->x, (RC)re);
+      atomicAdd(&p->y, (RC)im);
+    } else {
+      if (beta != (R)0) {
+        TC old = *p;
+        re += beta * (R)old.x;
+        im += beta * (R)old.y;
+      }
+      TC o;
+      o.x = (RC)re;
+      o.y = (RC)im;
+      *p = o;
+    }
+    if (d.hermitian && tm != tn) {   // mirror: C[j,i] = conj(C[i,j])
+      TC* q = Cb + map_idx(d.Ci, j) + map_idx(d.Cj, i);
       if (ksplit > 1) {
-        atomicAdd(&p->x, (RC)re);
-        atomicAdd(&p->y, (RC)im);
+        atomicAdd(&q->x, (RC)re);
+        atomicAdd(&q->y, (RC)(-im));
       } else {
-        if (beta != (R)0) {
-          TC old = *p;
-          re += beta * (R)old.x;
-          im += beta * (R)old.y;
-        }
         TC o;
         o.x = (RC)re;
-        o.y = (RC)im;
-        *p = o;
+        o.y = (RC)(-im);
+        *q = o;
       }
-      if (d.hermitian && tm != tn) {   // mirror: C[j,i] = conj(C[i,j])
-        TC* q = Cb + map_idx(d.Ci, j0 + tx + 16 * v) + map_idx(d.Cj, i);
-        if (ksplit > 1) {
-          atomicAdd(&q->x, (RC)re);
-          atomicAdd(&q->y, (RC)(-im));
-        } else {
-          TC o;
-          o.x = (RC)re;
-          o.y = (RC)(-im);
-          *q = o;
+    }
+  };
+
+  if constexpr (MMA) {
+    // ---- fp64 tensor pipe: warp tile 16 (M) x 32 (N) complex = 2 x 4 DMMA blocks, re and im accumulators -------
+    const int warp = tid >> 5, lane = tid & 31;
+    const int wm = warp & 3, wn = warp >> 2;
+    const int fr = lane >> 2, fk = lane & 3;
+    double accRe[2][4][2], accIm[2][4][2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) {
+        accRe[u][v][0] = accRe[u][v][1] = 0.0;
+        accIm[u][v][0] = accIm[u][v][1] = 0.0;
+      }
+    if (kBeg < kEnd) {
+      load_tile(kBeg);
+      store_tile();
+      __syncthreads();
+      for (int k0 = kBeg; k0 < kEnd; k0 += BK) {
+        const bool more = (k0 + BK) < kEnd;
+        if (more) load_tile(k0 + BK);
+#pragma unroll
+        for (int k4 = 0; k4 < BK; k4 += 4) {
+          CR a[2], bb[4];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) a[u] = As[k4 + fk][wm * 16 + u * 8 + fr];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) bb[v] = Bs[k4 + fk][wn * 32 + v * 8 + fr];
+#pragma unroll
+          for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              dmma(accRe[u][v], a[u].x, bb[v].x);
+              dmma(accIm[u][v], a[u].x, bb[v].y);
+            }
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const double nai = -a[u].y;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              dmma(accRe[u][v], nai, bb[v].y);
+              dmma(accIm[u][v], a[u].y, bb[v].x);
+            }
+          }
         }
+        __syncthreads();
+        if (more) {
+          store_tile();
+          __syncthreads();
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int i = i0 + wm * 16 + u * 8 + fr;
+      if (i >= d.M) continue;
+      const long long oi = map_idx(d.Ci, i);
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int j = j0 + wn * 32 + v * 8 + 2 * fk + e;
+          if (j >= d.N) continue;
+          emit(i, j, oi, map_idx(d.Cj, j), (R)accRe[u][v][e], (R)accIm[u][v][e]);
+        }
+    }
+  } else {
+    CR acc[TM][TN];
+#pragma unroll
+    for (int u = 0; u < TM; ++u)
+#pragma unroll
+      for (int v = 0; v < TN; ++v) {
+        acc[u][v].x = 0;
+        acc[u][v].y = 0;
+      }
+
+    if (kBeg < kEnd) {
+      load_tile(kBeg);
+      store_tile();
+      __syncthreads();
+      for (int k0 = kBeg; k0 < kEnd; k0 += BK) {
+        const bool more = (k0 + BK) < kEnd;
+        if (more) load_tile(k0 + BK);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+          CR a[TM], bb[TN];
+#pragma unroll
+          for (int u = 0; u < TM; ++u) a[u] = As[kk][ty + 16 * u];
+#pragma unroll
+          for (int v = 0; v < TN; ++v) bb[v] = Bs[kk][tx + 16 * v];
+#pragma unroll
+          for (int u = 0; u < TM; ++u)
+#pragma unroll
+            for (int v = 0; v < TN; ++v) cfma(acc[u][v], a[u], bb[v]);
+        }
+        __syncthreads();
+        if (more) {
+          store_tile();
+          __syncthreads();
+        }
+      }
+    }
+
+    long long offCj[TN];
+#pragma unroll
+    for (int v = 0; v < TN; ++v) {
+      int j = j0 + tx + 16 * v;
+      offCj[v] = (j < d.N) ? map_idx(d.Cj, j) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < TM; ++u) {
+      int i = i0 + ty + 16 * u;
+      if (i >= d.M) continue;
+      long long oi = map_idx(d.Ci, i);
+#pragma unroll
+      for (int v = 0; v < TN; ++v) {
+        if (offCj[v] < 0) continue;
+        emit(i, j0 + tx + 16 * v, oi, offCj[v], acc[u][v].x, acc[u][v].y);
       }
     }
   }
 }
 
-template <typename TA, typename TB, typename TC, typename R>
+template <typename TA, typename TB, typename TC, typename R, bool MMA = false>
 static int launch_contract(const mpdo_contract_desc& d, const void* A, const void* B, void* C, cudaStream_t st) {
   const int tilesM = (d.M + BM - 1) / BM, tilesN = (d.N + BN - 1) / BN;
   const int ksplit = d.ksplit > 1 ? d.ksplit : 1;
@@ -229,7 +320,7 @@ static int launch_contract(const mpdo_contract_desc& d, const void* A, const voi
     const double byts = (double)d.batch * ((double)d.M * d.K * sizeof(TA) + (double)d.K * d.N * sizeof(TB) +
                                            (double)d.M * d.N * sizeof(TC));
     TimedLaunch timed(0, 8.0 * mnk, byts, st);   // algorithmic cost of a complex contraction
-    contract_kernel<TA, TB, TC, R><<<(unsigned)grid, NT, 0, st>>>(d, (const TA*)A, (const TB*)B, (TC*)C, tilesM,
+    contract_kernel<TA, TB, TC, R, MMA><<<(unsigned)grid, NT, 0, st>>>(d, (const TA*)A, (const TB*)B, (TC*)C, tilesM,
                                                                     tilesN, kChunk);
   }
   return check_launch("contract_kernel");
@@ -249,6 +340,25 @@ extern "C" int mpdo_contract(const mpdo_contract_desc* dp, const void* A, const 
   const int key = (d.dtypeA << 2) | (d.dtypeB << 1) | d.dtypeC;
   const bool f64 = d.acc64 || key != 0;
   if (!f64) return launch_contract<float2, float2, float2, float>(d, A, B, C, st);
+  // Measured on B200 (tools/bench_contract.py): the DMMA tiles are 6 % faster than the scalar DFMA tiles when an
+  // operand is complex128 (21.8 vs 20.6 TFLOP/s on 512 x 8192 x 512) and 18 % slower on complex64 x complex64 Gram
+  // matrices (12.7 vs 15.4 TFLOP/s on 1024 x 1024 x 8192): B200 retires DMMA on the same fp64 units as DFMA, so the
+  // tensor form only saves issue slots. Default: DMMA iff an input operand is complex128.
+  // MPDO_NO_DMMA=1 / MPDO_DMMA_ALL=1 force one kernel for A/B comparisons.
+  static const bool noDmma = getenv("MPDO_NO_DMMA") != nullptr;
+  static const bool allDmma = getenv("MPDO_DMMA_ALL") != nullptr;
+  if (!noDmma && (allDmma || key >= 2)) {
+    switch (key) {
+      case 0: return launch_contract<float2, float2, float2, double, true>(d, A, B, C, st);
+      case 1: return launch_contract<float2, float2, double2, double, true>(d, A, B, C, st);
+      case 2: return launch_contract<float2, double2, float2, double, true>(d, A, B, C, st);
+      case 3: return launch_contract<float2, double2, double2, double, true>(d, A, B, C, st);
+      case 4: return launch_contract<double2, float2, float2, double, true>(d, A, B, C, st);
+      case 5: return launch_contract<double2, float2, double2, double, true>(d, A, B, C, st);
+      case 6: return launch_contract<double2, double2, float2, double, true>(d, A, B, C, st);
+      case 7: return launch_contract<double2, double2, double2, double, true>(d, A, B, C, st);
+    }
+  }
   switch (key) {
     case 0: return launch_contract<float2, float2, float2, double>(d, A, B, C, st);
     case 1: return launch_contract<float2, float2, double2, double>(d, A, B, C, st);

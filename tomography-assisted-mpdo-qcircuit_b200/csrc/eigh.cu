@@ -227,8 +227,9 @@ static size_t chol_smem(int n, int R, bool inverse) {
   return chol_ws_offset(n, R) + (inverse ? (size_t)R * n * sizeof(double2) : 0);
 }
 
-// rows per CTA / CTAs per matrix, or false when the batch cannot be made co-resident
-static bool chol_plan(int batch, int n, bool inverse, int* Rout, int* Cout) {
+// rows per CTA / CTAs per matrix and the number of matrices one launch can hold co-resident (a batch beyond that is
+// factorised in consecutive launches of `chunk` matrices), or false when not even one matrix can be scheduled
+static bool chol_plan(int batch, int n, bool inverse, int* Rout, int* Cout, int* chunkOut) {
   static int smemMax = 0, sms = 0, coop = 0;
   if (!smemMax) {
     int dev = 0;
@@ -243,12 +244,14 @@ static bool chol_plan(int batch, int n, bool inverse, int* Rout, int* Cout) {
     }
   }
   const size_t cap = (size_t)smemMax - 1024;
+  *chunkOut = batch;
   if (chol_smem(n, n, inverse) <= cap) {   // whole factor in one CTA
     *Rout = n;
     *Cout = 1;
     return true;
   }
   if (!coop) return false;
+  int bestR = 0, bestC = 0, bestChunk = 0;
   for (int R = 8; R < n; R *= 2) {
     const size_t sm = chol_smem(n, R, inverse);
     if (sm > cap) break;
@@ -258,13 +261,23 @@ static bool chol_plan(int batch, int n, bool inverse, int* Rout, int* Cout) {
       cudaGetLastError();
       return false;
     }
-    if ((long long)C * batch <= (long long)perSm * sms) {
+    const long long capacity = (long long)perSm * sms;
+    if ((long long)C * batch <= capacity) {   // the whole batch at the widest spread that fits
       *Rout = R;
       *Cout = C;
       return true;
     }
+    if (capacity >= C) {   // remember the plan with the most matrices per launch (fewest CTAs per matrix)
+      bestR = R;
+      bestC = C;
+      bestChunk = (int)(capacity / C);
+    }
   }
-  return false;
+  if (!bestR) return false;
+  *Rout = bestR;
+  *Cout = bestC;
+  *chunkOut = bestChunk;
+  return true;
 }
 
 struct EighLayout {
@@ -304,19 +317,10 @@ namespace mpdo {
 // Returns 1 when the shape cannot be scheduled (caller falls back), 0 on success, other values on CUDA errors.
 static int chol_launch(int batch, int n, const void* G, void* Y, void* X, void* slotsBase, size_t slotsBytes,
                        int* info, double rel, cudaStream_t st, int* rcOut) {
-  int R = 0, C = 0;
+  int R = 0, C = 0, chunk = 0;
   *rcOut = 0;
-  if (!chol_plan(batch, n, X != nullptr, &R, &C)) return 1;
+  if (!chol_plan(batch, n, X != nullptr, &R, &C, &chunk)) return 1;
   if (C > 1 && (size_t)batch * 2 * C * (n + 1) * sizeof(double2) > slotsBytes) return 1;
-  CholArgs a;
-  a.n = n;
-  a.R = R;
-  a.rel = rel;
-  a.G = (const double2*)G;
-  a.Y = (double2*)Y;
-  a.X = (double2*)X;
-  a.slots = (double2*)slotsBase;
-  a.info = info;
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int) * 4 * (size_t)batch, st);
   if (e == cudaSuccess && X) e = cudaMemsetAsync(X, 0, sizeof(double2) * (size_t)batch * n * n, st);
   if (e != cudaSuccess) {
@@ -325,21 +329,33 @@ static int chol_launch(int batch, int n, const void* G, void* Y, void* X, void* 
     return 0;
   }
   const size_t smem = chol_smem(n, R, X != nullptr);
-  {
+  for (int b0 = 0; b0 < batch; b0 += chunk) {   // one launch unless the batch exceeds what can be co-resident
+    const int nb = batch - b0 < chunk ? batch - b0 : chunk;
+    const long long mat = (long long)b0 * n * n;
+    CholArgs a;
+    a.n = n;
+    a.R = R;
+    a.rel = rel;
+    a.G = (const double2*)G + mat;
+    a.Y = (double2*)Y + mat;
+    a.X = X ? (double2*)X + mat : nullptr;
+    a.slots = (double2*)slotsBase + (long long)b0 * 2 * C * (n + 1);
+    a.info = info + 4LL * b0;
     TimedLaunch timed(2, 0.0, 0.0, st);
     if (C == 1) {
-      chol_kernel<<<dim3(1, batch), CHOL_THREADS, smem, st>>>(a);
+      chol_kernel<<<dim3(1, nb), CHOL_THREADS, smem, st>>>(a);
     } else {
       void* args[] = {(void*)&a};
-      e = cudaLaunchCooperativeKernel((const void*)chol_kernel, dim3(C, batch), dim3(CHOL_THREADS), args, smem, st);
+      e = cudaLaunchCooperativeKernel((const void*)chol_kernel, dim3(C, nb), dim3(CHOL_THREADS), args, smem, st);
       if (e != cudaSuccess) {
         snprintf(g_err, sizeof(g_err), "chol_kernel (cooperative): %s", cudaGetErrorString(e));
         *rcOut = (int)e;
         return 0;
       }
     }
+    *rcOut = check_launch("chol_kernel");
+    if (*rcOut) return 0;
   }
-  *rcOut = check_launch("chol_kernel");
   return 0;
 }
 

@@ -265,11 +265,13 @@ struct Ctx {
     use_chol = !noChol;
   }
   bool use_chol = true;
-  // Large batches (parameter sweeps, cfg4) already fill the GPU with one CTA group per matrix; measured on a
-  // 128-circuit chunk the classic batched Jacobi route is 1.4x faster there than factorising first, because the
-  // pivoted Cholesky of matrices beyond one CTA's shared memory needs co-resident CTA groups that a batch cannot have.
+  // Large batches (parameter sweeps, cfg4): the factorisations that need co-resident CTA groups (pivoted Cholesky
+  // and persistent Jacobi beyond one CTA's shared memory) walk the batch in co-resident chunks, so a batch takes the
+  // same Cholesky-QR / preconditioned routes as a single circuit. MPDO_BATCH_CLASSIC=1 restores the first policy
+  // of the round (classic Jacobi on [G | I] for B >= 32) for A/B measurements.
   void set_batch(long long B) {
-    if (B >= 32) {
+    static const bool classic = getenv("MPDO_BATCH_CLASSIC") != nullptr;
+    if (classic && B >= 32) {
       use_chol = false;
       precondition = false;
     }

@@ -745,9 +745,15 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
     // 371 ms where the multi-launch driver below takes 206 ms, so sharing is opt-in (MPDO_JACOBI_SHARE) and the
     // persistent kernel is used when every block pair of a round gets its own CTA.
     static const bool share = getenv("MPDO_JACOBI_SHARE") != nullptr;
+    // A batch too large to be co-resident with one CTA per block pair is walked in consecutive cooperative launches
+    // of `chunk` matrices each (every launch still runs all sweeps of its matrices on the device, no host polling).
+    static const bool noChunk = getenv("MPDO_JACOBI_NOCHUNK") != nullptr;   // A/B knob: multi-launch driver instead
+    int chunk = batch;
+    if (P < nbp / 2 && !share && !noChunk && capacity >= nbp / 2) {
+      chunk = (int)(capacity / (nbp / 2));
+      P = nbp / 2;
+    }
     if (fn && perSm > 0 && coop && (P == nbp / 2 || (share && P >= 1))) {
-      TimedLaunch timed(1, 0.0, 0.0, st);
-      void* args[] = {(void*)&a, (void*)&Y};
       unsigned nthreads = threads;
       static const bool noReg = getenv("MPDO_JACOBI_NOREG") != nullptr;   // debugging knob
       if (!noReg && P == nbp / 2 && mt > 256 && mt <= 512 && b <= 16) {
@@ -757,17 +763,33 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
         fn = (const void*)jacobi_persistent_reg_kernel<16, 512>;
         nthreads = 32u * (unsigned)b;
       }
-      cudaError_t e;
-      if (P > 1) {
-        e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)P, batch), dim3(nthreads), args, smem, st);
-      } else {
-        e = cudaLaunchKernel(fn, dim3(1, batch), dim3(nthreads), args, smem, st);
+      bool ok = true;
+      for (int b0 = 0; b0 < batch && ok; b0 += chunk) {
+        const int nbat = batch - b0 < chunk ? batch - b0 : chunk;
+        JacobiArgs ac = a;
+        ac.cnt = work + (long long)b0 * WORK_INTS;
+        ac.rank = rank ? rank + (long long)b0 * rankStride : nullptr;
+        double2* Yc = (double2*)Y + (long long)b0 * batchStride;
+        void* args[] = {(void*)&ac, (void*)&Yc};
+        TimedLaunch timed(1, 0.0, 0.0, st);
+        cudaError_t e;
+        if (P > 1) {
+          e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)P, nbat), dim3(nthreads), args, smem, st);
+        } else {
+          e = cudaLaunchKernel(fn, dim3(1, nbat), dim3(nthreads), args, smem, st);
+        }
+        if (e == cudaSuccess) {
+          ++g_launches;
+        } else {
+          cudaGetLastError();   // e.g. cudaErrorCooperativeLaunchTooLarge
+          ok = false;
+          if (b0 > 0) {   // earlier chunks already ran: the multi-launch driver below must not redo them
+            snprintf(g_err, sizeof(g_err), "jacobi_persistent (chunk %d): %s", b0, cudaGetErrorString(e));
+            return (int)e;
+          }
+        }
       }
-      if (e == cudaSuccess) {
-        ++g_launches;
-        return 0;
-      }
-      cudaGetLastError();   // e.g. cudaErrorCooperativeLaunchTooLarge: fall through to the multi-launch driver
+      if (ok) return 0;   // first launch refused: fall through to the multi-launch driver
     }
   }
   for (int sw = 0; sw < maxSweeps; ++sw) {
