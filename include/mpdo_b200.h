@@ -195,6 +195,10 @@ int mpdo_timing_summary(int cls, double minFlops, double* seconds, double* flops
  * to the driver. The step functions return cudaErrorMemoryAllocation (2) only after trying this themselves; a caller
  * that shares the device with another caching allocator (torch) releases that cache and retries. */
 int mpdo_trim_pools(void);
+/* Bytes the scratch pool of the current device holds from the driver right now / at its high-water mark (the pool is
+ * pre-grown once at first use, MPDO_SCRATCH_PREWARM_MB, default 16 GiB; a high-water mark above that means the
+ * workload outgrew the pre-grown block). Either pointer may be NULL. */
+int mpdo_pool_stats(int64_t* reservedBytes, int64_t* reservedHighBytes);
 
 /* Library / device information. */
 int mpdo_version(void);

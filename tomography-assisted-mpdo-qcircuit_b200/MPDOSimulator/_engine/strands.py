@@ -17,7 +17,7 @@ import torch
 _POOL = None
 _STREAMS = {}
 _LOCK = threading.Lock()
-MAX_WORKERS = 12
+MAX_WORKERS = int(os.environ.get('MPDO_STRAND_WORKERS', '12'))   # tuning knob
 
 
 def _pool():
@@ -27,12 +27,32 @@ def _pool():
     return _POOL
 
 
+PREWARM_SMALL_MB = int(os.environ.get('MPDO_STRAND_PREWARM_MB', '48'))   # per stream; 0 disables
+
+
+def _prewarm(device, stream):
+    """Fills the caching allocator's small-block pool of `stream` once. Blocks handed between streams are released
+    through record_stream events, so whether a strand finds a free small block depends on timing; when it does not,
+    the allocator calls cudaMalloc for another 2 MB segment, and a cudaMalloc issued while persistent (barrier)
+    kernels of other strands are running was measured to stall every launching thread for 50-400 ms
+    (tools/prof_outliers.py: the occasional 2-3x slower step). A few dozen MB of cached segments per stream make
+    that path cold in steady state."""
+    if PREWARM_SMALL_MB <= 0:
+        return
+    with torch.cuda.device(device), torch.cuda.stream(stream):
+        blocks = [torch.empty(1 << 20, dtype=torch.uint8, device=device) for _ in range(PREWARM_SMALL_MB)]
+        del blocks
+
+
 def _streams(device, count):
     key = str(device)
     with _LOCK:
         have = _STREAMS.setdefault(key, [])
+        if not have:
+            _prewarm(device, torch.cuda.current_stream(device))
         while len(have) < count:
             have.append(torch.cuda.Stream(device=device))
+            _prewarm(device, have[-1])
         return have[:count]
 
 

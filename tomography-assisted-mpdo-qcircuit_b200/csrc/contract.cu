@@ -113,7 +113,6 @@ __global__ void __launch_bounds__(NT, MMA ? 1 : 2) contract_kernel(const mpdo_co
       v.y = 0;
       if (k < kEnd && offAi[r] >= 0) {
         v = Ab[offAi[r] + map_idx(d.Ak, k)];
-        if (d.conjA) v.y = -v.y;
       }
       ra[r] = v;
     }
@@ -125,25 +124,32 @@ __global__ void __launch_bounds__(NT, MMA ? 1 : 2) contract_kernel(const mpdo_co
       v.y = 0;
       if (k < kEnd && offBj[r] >= 0) {
         v = Bb[offBj[r] + map_idx(d.Bk, k)];
-        if (d.conjB) v.y = -v.y;
       }
       rb[r] = v;
     }
   };
+  // Conjugation happens here, not in load_tile: anything that consumes a loaded value there makes the warp wait
+  // for the load at once (ncu: a third of all stall samples sat on the sign flip right behind the LDG) instead of
+  // after the slab's arithmetic.
+  const R sgnA = d.conjA ? (R)-1 : (R)1, sgnB = d.conjB ? (R)-1 : (R)1;
   auto store_tile = [&]() {
 #pragma unroll
     for (int r = 0; r < LA; ++r) {
+      CR v = cconv<CR>(ra[r]);
+      v.y *= sgnA;
       if (akf)
-        As[a_kk][a_ii + r * (NT / BK)] = cconv<CR>(ra[r]);
+        As[a_kk][a_ii + r * (NT / BK)] = v;
       else
-        As[a_kk + r * (NT / BM)][a_ii] = cconv<CR>(ra[r]);
+        As[a_kk + r * (NT / BM)][a_ii] = v;
     }
 #pragma unroll
     for (int r = 0; r < LB; ++r) {
+      CR v = cconv<CR>(rb[r]);
+      v.y *= sgnB;
       if (bjf)
-        Bs[b_kk + r * (NT / BN)][b_jj] = cconv<CR>(rb[r]);
+        Bs[b_kk + r * (NT / BN)][b_jj] = v;
       else
-        Bs[b_kk][b_jj + r * (NT / BK)] = cconv<CR>(rb[r]);
+        Bs[b_kk][b_jj + r * (NT / BK)] = v;
     }
   };
 
@@ -340,14 +346,12 @@ extern "C" int mpdo_contract(const mpdo_contract_desc* dp, const void* A, const 
   const int key = (d.dtypeA << 2) | (d.dtypeB << 1) | d.dtypeC;
   const bool f64 = d.acc64 || key != 0;
   if (!f64) return launch_contract<float2, float2, float2, float>(d, A, B, C, st);
-  // Measured on B200 (tools/bench_contract.py): the DMMA tiles are 6 % faster than the scalar DFMA tiles when an
-  // operand is complex128 (21.8 vs 20.6 TFLOP/s on 512 x 8192 x 512) and 18 % slower on complex64 x complex64 Gram
-  // matrices (12.7 vs 15.4 TFLOP/s on 1024 x 1024 x 8192): B200 retires DMMA on the same fp64 units as DFMA, so the
-  // tensor form only saves issue slots. Default: DMMA iff an input operand is complex128.
-  // MPDO_NO_DMMA=1 / MPDO_DMMA_ALL=1 force one kernel for A/B comparisons.
+  // Measured on B200 (tools/bench_contract.py, profiles/r1_contract_ncu.md): DMMA tiles 18.1 TFLOP/s on the kappa
+  // Gram matrix (1024 x 1024 x 8192, complex64 in, fp64 accumulate) and 26.5 TFLOP/s on a complex128-operand apply
+  // (512 x 8192 x 512), scalar DFMA tiles 16.5 and 22.0. B200 retires DMMA at about the DFMA rate, so the tensor form
+  // only frees issue slots and registers. MPDO_NO_DMMA=1 forces the scalar kernel for A/B comparisons.
   static const bool noDmma = getenv("MPDO_NO_DMMA") != nullptr;
-  static const bool allDmma = getenv("MPDO_DMMA_ALL") != nullptr;
-  if (!noDmma && (allDmma || key >= 2)) {
+  if (!noDmma) {
     switch (key) {
       case 0: return launch_contract<float2, float2, float2, double, true>(d, A, B, C, st);
       case 1: return launch_contract<float2, float2, double2, double, true>(d, A, B, C, st);
