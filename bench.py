@@ -228,6 +228,10 @@ def b200_arm(args):
     # cost of the process, not throughput of the path.
     for d in range(P + W, P + W + K):
         circuits[d][0].evolve(state)
+    if world > 1:   # the exchange step too: the first NCCL collective of a process sets the communicator up
+        readout = circuits[P + W + K - 1][0].bitstring_probabilities(['0' * n]).to(torch.float64).reshape(1)
+        gathered = torch.empty(world, dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(gathered, readout)
     barrier()
     for s, snap in zip(state, snapshot):
         s.data = snap.clone()
@@ -352,7 +356,8 @@ def b200_arm(args):
         ct, cf = max(t_contract['seconds'], 1e-30), t_contract['flops']
         roof = {
             'bound': 'tensor',
-            'kernel': 'contract_kernel (batched complex contraction, FP32 FFMA / FP64 DFMA SIMT tiles), all launches',
+            'kernel': 'contract_kernel (batched complex contraction: fp64-accumulated launches on DMMA m8n8k4 tensor '
+                      'tiles, complex64 applies on FP32 FFMA tiles), all launches',
             'achieved': cf / ct / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': cf / ct / 1e12 / peak_tf,
             'traffic': None, 'peak_source': peak_src,
             'launches_timed': t_contract['launches'], 'kernel_seconds': ct, 'share_of_step_device_time': None,
@@ -364,10 +369,22 @@ def b200_arm(args):
             'note': 'algorithmic flops = 8*M*N*K per complex contraction (SURVEY 8d), every launch timed with CUDA '
                     'events on its own stream in a replay of the timed layers from the same state (the value / e2e '
                     'passes run without the per-launch events); the denominator is the dense bf16 tensor peak although '
-                    'the kernel must deliver fp32/fp64-accurate complex arithmetic (FFMA/DFMA), most of it fp64-'
-                    'accumulated Gram matrices. Device time is split between this kernel and the two latency-bound '
+                    'the kernel must deliver fp32/fp64-accurate complex arithmetic (FFMA / fp64 DMMA), most of it fp64-'
+                    'accumulated Gram matrices whose own ceiling is the fp64 pipe (largest_launch.frac_of_fp64_pipe). Device time is split between this kernel and the two latency-bound '
                     'factorisation kernels (see factorisation_kernels).',
         }
+        # DRAM traffic of the largest contraction launch (the kappa Gram matrix) from the committed `ncu --set full`
+        # capture, next to its algorithmic bytes; and the same launch against the fp64 pipe it actually runs on
+        tr = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+        if os.path.exists(tr):
+            t = json.load(open(tr))
+            roof['traffic'] = t['dram_read_bytes'] + t['dram_write_bytes']
+            roof['traffic_detail'] = {k: t[k] for k in ('launch', 'dram_read_bytes', 'dram_write_bytes',
+                                                        'algorithmic_bytes', 'source')}
+        sm_ghz = (peaks.get('sm_max_mhz') or 1965.0) / 1e3
+        fp64_peak = 148 * 64 * 2 * sm_ghz / 1e3   # TFLOP/s: 64 fp64 FMA lanes per SM per clock
+        roof['largest_launch']['frac_of_fp64_pipe'] = roof['largest_launch']['TFLOP/s'] / fp64_peak
+        roof['largest_launch']['fp64_pipe_peak_TFLOP/s'] = fp64_peak
         jt = max(t_jacobi['seconds'], 1e-30)
         ht = max(t_chol['seconds'], 1e-30)
         roof['share_of_step_device_time'] = ct / (ct + jt + ht)

@@ -130,9 +130,12 @@ def test_eigh_psd_rank_deficient_and_degenerate(cuda_prims):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize('n,rk,Bn', [(1, 1, 2), (2, 2, 3), (24, 24, 5), (40, 7, 2), (100, 60, 3), (113, 113, 2),
-                                     (130, 90, 2), (256, 256, 1), (400, 300, 1), (512, 512, 1)])
+                                     (130, 90, 2), (256, 256, 1), (400, 300, 1), (512, 512, 1),
+                                     (160, 120, 80), (256, 200, 40)])
 def test_eigh_psd_rank_revealing(cuda_prims, n, rk, Bn):
-    """Pivoted-Cholesky preconditioned route: graded spectrum, numerical rank rk < n, batch."""
+    """Pivoted-Cholesky preconditioned route: graded spectrum, numerical rank rk < n, batch. The last two cases
+    are batches whose CTA groups cannot all be co-resident: the factorisation and the persistent Jacobi walk them in
+    chunks (parameter sweeps, cfg4)."""
     A = rnd((Bn, n, rk), C128, 21)
     A = A * torch.logspace(0, -5, rk, dtype=torch.float64)       # eigenvalues graded over ten decades
     G = A @ A.mH
@@ -171,7 +174,7 @@ def test_eigh_psd_rank_revealing_zero_and_identity(cuda_prims):
 
 
 @pytest.mark.parametrize('n,rk,Bn', [(1, 1, 2), (3, 2, 2), (24, 24, 4), (60, 31, 3), (84, 84, 1), (85, 85, 2),
-                                     (130, 70, 2), (256, 256, 1), (512, 400, 1)])
+                                     (130, 70, 2), (256, 256, 1), (512, 400, 1), (160, 100, 40), (256, 256, 24)])
 def test_chol_psd(cuda_prims, n, rk, Bn):
     """Pivoted Cholesky with left inverse: the two identities every Cholesky-QR step of the engine relies on."""
     A = rnd((Bn, n, rk), C128, 31)

@@ -26,7 +26,9 @@
 
 namespace mpdo {
 
-constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
+constexpr int BM = 64, BN = 64, BK = 16;
+// MMA = 0: scalar tiles, 256 threads; 1: DMMA, 8 warps with 16x32 warp tiles; 2: DMMA, 16 warps with 16x16 warp tiles
+__host__ __device__ constexpr int threads_of(int mma) { return mma == 2 ? 512 : 256; }
 constexpr int TM = BM / 16, TN = BN / 16;
 
 // D(8x8) += A(8x4, row) * B(4x8, col), fp64. Fragments: A: lane holds A[lane/4][lane%4]; B: lane holds B[lane%4][lane/4];
@@ -37,8 +39,8 @@ __device__ __forceinline__ void dmma(double (&c)[2], double a, double b) {
                : "d"(a), "d"(b));
 }
 
-template <typename TA, typename TB, typename TC, typename R, bool MMA>
-__global__ void __launch_bounds__(NT, MMA ? 1 : 2) contract_kernel(const mpdo_contract_desc d, const TA* __restrict__ A,
+template <typename TA, typename TB, typename TC, typename R, int MMA>
+__global__ void __launch_bounds__(threads_of(MMA), MMA ? 1 : 2) contract_kernel(const mpdo_contract_desc d, const TA* __restrict__ A,
                                                       const TB* __restrict__ B, TC* __restrict__ C, int tilesM,
                                                       int tilesN, int kChunk) {
   using CR = typename cplx<R>::type;
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(NT, MMA ? 1 : 2) contract_kernel(const mpdo_co
   const TB* Bb = B + map_idx(d.Bb, b);
 
   // ---- loader geometry -----------------------------------------------------------------------
+  constexpr int NT = threads_of(MMA);
   constexpr int LA = BM * BK / NT;  // elements of the A tile per thread
   constexpr int LB = BN * BK / NT;
   const bool akf = d.a_kfast != 0;
@@ -190,15 +193,16 @@ __global__ void __launch_bounds__(NT, MMA ? 1 : 2) contract_kernel(const mpdo_co
   };
 
   if constexpr (MMA) {
-    // ---- fp64 tensor pipe: warp tile 16 (M) x 32 (N) complex = 2 x 4 DMMA blocks, re and im accumulators -------
+    // ---- fp64 tensor pipe: warp tile 16 (M) x 8 NB (N) complex = 2 x NB DMMA blocks, re and im accumulators ------
+    constexpr int NB = MMA == 2 ? 2 : 4;   // 16 warps: 4 x 4 warps of 16 x 16; 8 warps: 4 x 2 warps of 16 x 32
     const int warp = tid >> 5, lane = tid & 31;
     const int wm = warp & 3, wn = warp >> 2;
     const int fr = lane >> 2, fk = lane & 3;
-    double accRe[2][4][2], accIm[2][4][2];
+    double accRe[2][NB][2], accIm[2][NB][2];
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
+      for (int v = 0; v < NB; ++v) {
         accRe[u][v][0] = accRe[u][v][1] = 0.0;
         accIm[u][v][0] = accIm[u][v][1] = 0.0;
       }
@@ -211,15 +215,15 @@ __global__ void __launch_bounds__(NT, MMA ? 1 : 2) contract_kernel(const mpdo_co
         if (more) load_tile(k0 + BK);
 #pragma unroll
         for (int k4 = 0; k4 < BK; k4 += 4) {
-          CR a[2], bb[4];
+          CR a[2], bb[NB];
 #pragma unroll
           for (int u = 0; u < 2; ++u) a[u] = As[k4 + fk][wm * 16 + u * 8 + fr];
 #pragma unroll
-          for (int v = 0; v < 4; ++v) bb[v] = Bs[k4 + fk][wn * 32 + v * 8 + fr];
+          for (int v = 0; v < NB; ++v) bb[v] = Bs[k4 + fk][wn * (8 * NB) + v * 8 + fr];
 #pragma unroll
           for (int u = 0; u < 2; ++u)
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
+            for (int v = 0; v < NB; ++v) {
               dmma(accRe[u][v], a[u].x, bb[v].x);
               dmma(accIm[u][v], a[u].x, bb[v].y);
             }
@@ -227,7 +231,7 @@ __global__ void __launch_bounds__(NT, MMA ? 1 : 2) contract_kernel(const mpdo_co
           for (int u = 0; u < 2; ++u) {
             const double nai = -a[u].y;
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
+            for (int v = 0; v < NB; ++v) {
               dmma(accRe[u][v], nai, bb[v].y);
               dmma(accIm[u][v], a[u].y, bb[v].x);
             }
@@ -246,10 +250,10 @@ __global__ void __launch_bounds__(NT, MMA ? 1 : 2) contract_kernel(const mpdo_co
       if (i >= d.M) continue;
       const long long oi = map_idx(d.Ci, i);
 #pragma unroll
-      for (int v = 0; v < 4; ++v)
+      for (int v = 0; v < NB; ++v)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const int j = j0 + wn * 32 + v * 8 + 2 * fk + e;
+          const int j = j0 + wn * (8 * NB) + v * 8 + 2 * fk + e;
           if (j >= d.N) continue;
           emit(i, j, oi, map_idx(d.Cj, j), (R)accRe[u][v][e], (R)accIm[u][v][e]);
         }
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(NT, MMA ? 1 : 2) contract_kernel(const mpdo_co
   }
 }
 
-template <typename TA, typename TB, typename TC, typename R, bool MMA = false>
+template <typename TA, typename TB, typename TC, typename R, int MMA = 0>
 static int launch_contract(const mpdo_contract_desc& d, const void* A, const void* B, void* C, cudaStream_t st) {
   const int tilesM = (d.M + BM - 1) / BM, tilesN = (d.N + BN - 1) / BN;
   const int ksplit = d.ksplit > 1 ? d.ksplit : 1;
@@ -326,7 +330,7 @@ static int launch_contract(const mpdo_contract_desc& d, const void* A, const voi
     const double byts = (double)d.batch * ((double)d.M * d.K * sizeof(TA) + (double)d.K * d.N * sizeof(TB) +
                                            (double)d.M * d.N * sizeof(TC));
     TimedLaunch timed(0, 8.0 * mnk, byts, st);   // algorithmic cost of a complex contraction
-    contract_kernel<TA, TB, TC, R, MMA><<<(unsigned)grid, NT, 0, st>>>(d, (const TA*)A, (const TB*)B, (TC*)C, tilesM,
+    contract_kernel<TA, TB, TC, R, MMA><<<(unsigned)grid, threads_of(MMA), 0, st>>>(d, (const TA*)A, (const TB*)B, (TC*)C, tilesM,
                                                                     tilesN, kChunk);
   }
   return check_launch("contract_kernel");
@@ -351,16 +355,29 @@ extern "C" int mpdo_contract(const mpdo_contract_desc* dp, const void* A, const 
   // (512 x 8192 x 512), scalar DFMA tiles 16.5 and 22.0. B200 retires DMMA at about the DFMA rate, so the tensor form
   // only frees issue slots and registers. MPDO_NO_DMMA=1 forces the scalar kernel for A/B comparisons.
   static const bool noDmma = getenv("MPDO_NO_DMMA") != nullptr;
+  static const bool dmma8 = getenv("MPDO_DMMA_8WARPS") != nullptr;   // A/B knob: 8-warp DMMA tiles
+  if (!noDmma && dmma8) {
+    switch (key) {
+      case 0: return launch_contract<float2, float2, float2, double, 1>(d, A, B, C, st);
+      case 1: return launch_contract<float2, float2, double2, double, 1>(d, A, B, C, st);
+      case 2: return launch_contract<float2, double2, float2, double, 1>(d, A, B, C, st);
+      case 3: return launch_contract<float2, double2, double2, double, 1>(d, A, B, C, st);
+      case 4: return launch_contract<double2, float2, float2, double, 1>(d, A, B, C, st);
+      case 5: return launch_contract<double2, float2, double2, double, 1>(d, A, B, C, st);
+      case 6: return launch_contract<double2, double2, float2, double, 1>(d, A, B, C, st);
+      case 7: return launch_contract<double2, double2, double2, double, 1>(d, A, B, C, st);
+    }
+  }
   if (!noDmma) {
     switch (key) {
-      case 0: return launch_contract<float2, float2, float2, double, true>(d, A, B, C, st);
-      case 1: return launch_contract<float2, float2, double2, double, true>(d, A, B, C, st);
-      case 2: return launch_contract<float2, double2, float2, double, true>(d, A, B, C, st);
-      case 3: return launch_contract<float2, double2, double2, double, true>(d, A, B, C, st);
-      case 4: return launch_contract<double2, float2, float2, double, true>(d, A, B, C, st);
-      case 5: return launch_contract<double2, float2, double2, double, true>(d, A, B, C, st);
-      case 6: return launch_contract<double2, double2, float2, double, true>(d, A, B, C, st);
-      case 7: return launch_contract<double2, double2, double2, double, true>(d, A, B, C, st);
+      case 0: return launch_contract<float2, float2, float2, double, 2>(d, A, B, C, st);
+      case 1: return launch_contract<float2, float2, double2, double, 2>(d, A, B, C, st);
+      case 2: return launch_contract<float2, double2, float2, double, 2>(d, A, B, C, st);
+      case 3: return launch_contract<float2, double2, double2, double, 2>(d, A, B, C, st);
+      case 4: return launch_contract<double2, float2, float2, double, 2>(d, A, B, C, st);
+      case 5: return launch_contract<double2, float2, double2, double, 2>(d, A, B, C, st);
+      case 6: return launch_contract<double2, double2, float2, double, 2>(d, A, B, C, st);
+      case 7: return launch_contract<double2, double2, double2, double, 2>(d, A, B, C, st);
     }
   }
   switch (key) {
