@@ -16,9 +16,22 @@
 // device-wide barrier, everybody reads the winner), then every warp finishes one entry of the new column with a
 // dot product against the pivot row (left-looking: no trailing-matrix traffic). Small matrices use C = 1 and no
 // barrier; batches of them run one CTA per matrix.
+//
+// Groups of up to 16 CTAs at 8 rows each (n <= 128) are launched as one thread-block cluster: candidates are
+// published in the CTA's own shared memory, the step barrier is the hardware cluster barrier, and the winner's row
+// of L is read straight out of the winning CTA's shared memory (DSMEM) - no global-memory slots, no L2 round trips,
+// and no cooperative launch, so any batch size is one launch. Larger groups (n = 512 with the inverse: 64 CTAs) keep
+// the device-wide barrier through L2 (see chol_cluster_plan for the measured crossover).
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <mutex>
+#include <utility>
+#include <vector>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mpdo {
 
@@ -30,6 +43,7 @@ struct CholArgs {
   double2* X;            // optional [batch][n][n], zeroed by the caller: X[k, piv_c] = (L11^-1)[k, c]
   double2* slots;        // [batch][2][C][n + 1] candidate exchange (C > 1 only)
   int* info;             // [batch][4]: rank, barrier counter, error flag, unused
+  int cluster;           // 1: the C CTAs of a matrix form one thread-block cluster (exchange through DSMEM)
 };
 
 constexpr int CHOL_THREADS = 256;
@@ -44,6 +58,9 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs p) {
   extern __shared__ double2 csm[];
   __shared__ double sVal;
   __shared__ int sIdx, sCta;
+  __shared__ double wbestV[32];   // per-warp best remaining diagonal / its local row
+  __shared__ int wbestI[32];
+  __shared__ double2 hdr[2];   // cluster mode: own candidate (value, global row) of the even / odd step
   const int n = p.n, R = p.R, C = (int)gridDim.x;
   const int c = blockIdx.x, bidx = blockIdx.y;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
@@ -69,43 +86,101 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs p) {
     chosen[r] = 0;
   }
   __syncthreads();
+  {   // per-warp best diagonal among the warp's rows (r = warp, warp + nwarps, ...)
+    double wb = -1.0;
+    int wi = 0x7fffffff;
+    for (int r = warp; r < rows; r += nwarps)
+      if (dl[r] > wb) {
+        wb = dl[r];
+        wi = r;
+      }
+    if (lane == 0) {
+      wbestV[warp] = wb;
+      wbestI[warp] = wi;
+    }
+  }
+  __syncthreads();
 
   double thresh = 0;
   int rank = n;
+#ifdef MPDO_CHOL_PROFILE   // nvcc -DMPDO_CHOL_PROFILE: CTA 0 of matrix 0 prints its cycles per phase of a step
+  long long tp[6] = {0, 0, 0, 0, 0, 0};
+  long long tc = clock64();
+#define CHOL_MARK(i)                 \
+  do {                               \
+    const long long now_ = clock64(); \
+    tp[i] += now_ - tc;              \
+    tc = now_;                       \
+  } while (0)
+#else
+#define CHOL_MARK(i)
+#endif
   for (int k = 0; k < n; ++k) {
-    // ---- own best candidate (ties: lowest row) ----
-    if (warp == 0) {
-      double best = -1.0;
-      int bi = 0x7fffffff;
-      for (int r = lane; r < rows; r += 32)
-        if (!chosen[r] && dl[r] > best) {
-          best = dl[r];
-          bi = r;
-        }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) {
-          best = ob;
-          bi = oi;
-        }
-      }
-      if (lane == 0) {
-        sVal = best;
-        sIdx = bi;
+    // ---- own best candidate (ties: lowest row): the per-warp bests were left in shared memory by the column
+    // phase of the previous step (or by the prologue), so this is nwarps broadcast reads, no shuffle tree ----
+    double cbest = -1.0;
+    int cidx = 0x7fffffff;
+    for (int w = 0; w < nwarps; ++w) {
+      const double v = wbestV[w];
+      const int i = wbestI[w];
+      if (v > cbest || (v == cbest && i < cidx)) {
+        cbest = v;
+        cidx = i;
       }
     }
-    __syncthreads();
-    double pval = sVal;
-    int pg = sIdx == 0x7fffffff ? -1 : row0 + sIdx;   // global row of the pivot
-    if (C > 1) {
-      const int li = sIdx;
+    CHOL_MARK(0);
+    double pval = cbest;
+    int pg = cidx == 0x7fffffff ? -1 : row0 + cidx;   // global row of the pivot
+    if (C > 1 && p.cluster) {
+      cg::cluster_group cl = cg::this_cluster();
+      if (tid == 0) hdr[k & 1] = make_double2(pval, (double)pg);
+      cl.sync();   // every CTA's candidate of this step is visible cluster-wide (and step k-1 is complete everywhere)
+      CHOL_MARK(1);
+      if (warp == 0) {
+        double best = -1.0;
+        int bc = 0x7fffffff, bg = -1;
+        for (int cc = lane; cc < C; cc += 32) {
+          const double2 h = *cl.map_shared_rank(&hdr[k & 1], cc);
+          if (h.y >= 0 && h.x > best) {
+            best = h.x;
+            bc = cc;
+            bg = (int)h.y;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+          const int og = __shfl_xor_sync(0xffffffffu, bg, o);
+          if (ob > best || (ob == best && oc < bc)) {
+            best = ob;
+            bc = oc;
+            bg = og;
+          }
+        }
+        if (lane == 0) {
+          sVal = best;
+          sCta = bc;
+          sIdx = bg;
+        }
+      }
+      __syncthreads();
+      CHOL_MARK(2);
+      pval = sVal;
+      pg = sIdx;
+      if (pg >= 0) {
+        // columns 0..k-1 of the winner's row are final (written in earlier steps), so they are read in place
+        const double2* wrow = cl.map_shared_rank(Ls + (size_t)(pg - sCta * R) * n, sCta);
+        for (int j = tid; j < k; j += blockDim.x) prow[j] = wrow[j];
+      }
+    } else if (C > 1) {
+      const int li = cidx;
       double2* mine = slots + ((long long)(k & 1) * C + c) * (n + 1);
       if (tid == 0) mine[0] = make_double2(pval, (double)pg);
       if (pg >= 0)
         for (int j = tid; j < k; j += blockDim.x) mine[1 + j] = Ls[(size_t)li * n + j];
       matrix_barrier(bar, (unsigned)C, phase, info + 2);
+      CHOL_MARK(1);
       if (warp == 0) {
         double best = -1.0;
         int bc = 0x7fffffff, bg = -1;
@@ -135,6 +210,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs p) {
         }
       }
       __syncthreads();
+      CHOL_MARK(2);
       pval = sVal;
       pg = sIdx;
       if (pg >= 0) {
@@ -142,22 +218,31 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs p) {
         for (int j = tid; j < k; j += blockDim.x) prow[j] = __ldcg(wrow + j);
       }
     } else if (pg >= 0) {
-      for (int j = tid; j < k; j += blockDim.x) prow[j] = Ls[(size_t)sIdx * n + j];
+      for (int j = tid; j < k; j += blockDim.x) prow[j] = Ls[(size_t)cidx * n + j];
     }
     if (k == 0) thresh = p.rel * pval;
-    if (pg < 0 || !(pval > thresh) || !(pval > 0.0) || *((volatile int*)(info + 2))) {   // same data in every CTA
+    if (pg < 0 || !(pval > thresh) || !(pval > 0.0) ||
+        (C > 1 && !p.cluster && *((volatile int*)(info + 2)))) {   // same data in every CTA
       rank = k;
       break;
     }
     __syncthreads();
+    CHOL_MARK(3);
     const double piv = sqrt(pval), inv = 1.0 / piv;
-    // ---- column k of L: one warp per own row ----
+    // ---- column k of L: one warp per own row; every lane carries the sums, so the warp also tracks the best
+    // remaining diagonal among its rows for the next step's pivot search ----
+    double wb = -1.0;
+    int wi = 0x7fffffff;
     for (int r = warp; r < rows; r += nwarps) {
       const int i = row0 + r;
+      const int wasChosen = chosen[r];
+      const double dold = dl[r];
+      __syncwarp();   // all lanes have read dl[r] / chosen[r] before lane 0 updates them
       double2 out = make_double2(0.0, 0.0);
+      double dnew = dold;
       if (i == pg) {
         out.x = piv;
-      } else if (!chosen[r]) {
+      } else if (!wasChosen) {
         double ar = 0, ai = 0;
         const double2* lrow = Ls + (size_t)r * n;
         for (int j = lane; j < k; j += 32) {   // L[i,j] * conj(L[p,j])
@@ -173,16 +258,26 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs p) {
         const double2 g = G[(long long)pg * n + i];   // G[i,p] = conj(G[p,i])
         out.x = (g.x - ar) * inv;
         out.y = (-g.y - ai) * inv;
+        dnew = fmax(dold - (out.x * out.x + out.y * out.y), 0.0);
+        if (dnew > wb) {   // rows ascend within a warp: ties keep the lowest row
+          wb = dnew;
+          wi = r;
+        }
       }
       if (lane == 0) {
         if (i == pg)
           chosen[r] = 1;
-        else if (!chosen[r])
-          dl[r] = fmax(dl[r] - (out.x * out.x + out.y * out.y), 0.0);
+        else if (!wasChosen)
+          dl[r] = dnew;
         Ls[(size_t)r * n + k] = out;
         Y[(long long)k * n + i] = make_double2(out.x, -out.y);
       }
     }
+    if (lane == 0) {
+      wbestV[warp] = wb;
+      wbestI[warp] = wi;
+    }
+    CHOL_MARK(4);
     if (X) {
       // Row k of W = L11^-1 (both indices in pivot order), column c owned by CTA c % C:
       //   W[k,k] = 1/piv,  W[k,c] = -(sum_{c<=j<k} L[p_k,j] W[j,c]) / piv
@@ -213,7 +308,15 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs p) {
       }
     }
     __syncthreads();
+    CHOL_MARK(5);
   }
+#ifdef MPDO_CHOL_PROFILE
+  if (c == 0 && bidx == 0 && tid == 0)
+    printf("[chol n=%d C=%d R=%d cluster=%d rank=%d] cycles/step: argmax %lld  barrier %lld  headers %lld  pivot-row %lld  column %lld  inverse+sync %lld\n",
+           n, C, R, p.cluster, rank, tp[0] / max(rank, 1), tp[1] / max(rank, 1), tp[2] / max(rank, 1), tp[3] / max(rank, 1),
+           tp[4] / max(rank, 1), tp[5] / max(rank, 1));
+#endif
+  if (C > 1 && p.cluster) cg::this_cluster().sync();   // nobody leaves while a neighbour may still read its rows
   // rows of Y beyond the rank are zero
   const long long tail = (long long)(n - rank) * rows;
   for (long long idx = tid; idx < tail; idx += blockDim.x) {
@@ -280,6 +383,68 @@ static bool chol_plan(int batch, int n, bool inverse, int* Rout, int* Cout, int*
   return true;
 }
 
+// Cluster plan: the widest spread of at most 16 CTAs per matrix whose rows fit shared memory, checked once per shape
+// against the device (cudaOccupancyMaxActiveClusters). Cluster sizes above 8 are non-portable and opted into.
+static bool chol_cluster_plan(int n, bool inverse, int* Rout, int* Cout) {
+  static const bool off = getenv("MPDO_CHOL_NOCLUSTER") != nullptr;   // A/B knob: device-wide barrier through L2
+  if (off) return false;
+  static int smemMax = 0;
+  if (!smemMax) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      smemMax = -1;
+    }
+  }
+  if (smemMax <= 0) return false;
+  const size_t cap = (size_t)smemMax - 1024;
+  {
+    // Only the widest spread (R = 8 rows per CTA, one row per warp) is worth a cluster: measured on B200, n = 128
+    // (16 CTAs) 0.450 ms against 0.522 ms through L2, but n = 256 as 16 CTAs x 16 rows 1.242 ms against 1.079 ms as
+    // 32 CTAs x 8 rows through L2 - the per-step column and inverse phases grow with the rows a CTA owns and outweigh
+    // the cheaper barrier. So: clusters for n <= 128, the L2 barrier beyond.
+    const int R = 8;
+    const int C = (n + R - 1) / R;
+    if (C > 16 || C < 2) return false;
+    const size_t sm = chol_smem(n, R, inverse);
+    if (sm > cap) return false;
+    // one query per (C, shared memory) pair; the answer does not change while the process lives
+    static std::mutex mu;
+    static std::vector<std::pair<std::pair<int, size_t>, int>> seen;
+    std::lock_guard<std::mutex> lk(mu);
+    int ok = -1;
+    for (auto& e : seen)
+      if (e.first.first == C && e.first.second == sm) ok = e.second;
+    if (ok < 0) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(C, 1);
+      cfg.blockDim = dim3(CHOL_THREADS);
+      cfg.dynamicSmemBytes = sm;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = C;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, chol_kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        nclusters = 0;
+      }
+      ok = nclusters >= 1 ? 1 : 0;
+      seen.push_back({{C, sm}, ok});
+    }
+    if (!ok) return false;
+    *Rout = R;
+    *Cout = C;
+    return true;
+  }
+}
+
 struct EighLayout {
   size_t y, slots, info, work, total;
 };
@@ -319,8 +484,17 @@ static int chol_launch(int batch, int n, const void* G, void* Y, void* X, void* 
                        int* info, double rel, cudaStream_t st, int* rcOut) {
   int R = 0, C = 0, chunk = 0;
   *rcOut = 0;
-  if (!chol_plan(batch, n, X != nullptr, &R, &C, &chunk)) return 1;
-  if (C > 1 && (size_t)batch * 2 * C * (n + 1) * sizeof(double2) > slotsBytes) return 1;
+  bool cluster = false;
+  int optin = 0, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const bool oneCta = optin > 1024 && chol_smem(n, n, X != nullptr) <= (size_t)optin - 1024;
+  if (!oneCta && chol_cluster_plan(n, X != nullptr, &R, &C)) {
+    cluster = true;   // more than one CTA per matrix, at most 16: one thread-block cluster each, any batch size
+    chunk = batch;
+  } else {
+    if (!chol_plan(batch, n, X != nullptr, &R, &C, &chunk)) return 1;
+    if (C > 1 && (size_t)batch * 2 * C * (n + 1) * sizeof(double2) > slotsBytes) return 1;
+  }
   cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int) * 4 * (size_t)batch, st);
   if (e == cudaSuccess && X) e = cudaMemsetAsync(X, 0, sizeof(double2) * (size_t)batch * n * n, st);
   if (e != cudaSuccess) {
@@ -341,8 +515,28 @@ static int chol_launch(int batch, int n, const void* G, void* Y, void* X, void* 
     a.X = X ? (double2*)X + mat : nullptr;
     a.slots = (double2*)slotsBase + (long long)b0 * 2 * C * (n + 1);
     a.info = info + 4LL * b0;
+    a.cluster = cluster ? 1 : 0;
     TimedLaunch timed(2, 0.0, 0.0, st);
-    if (C == 1) {
+    if (cluster) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(C, nb);
+      cfg.blockDim = dim3(CHOL_THREADS);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = C;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      e = cudaLaunchKernelEx(&cfg, chol_kernel, a);
+      if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "chol_kernel (cluster of %d): %s", C, cudaGetErrorString(e));
+        *rcOut = (int)e;
+        return 0;
+      }
+    } else if (C == 1) {
       chol_kernel<<<dim3(1, nb), CHOL_THREADS, smem, st>>>(a);
     } else {
       void* args[] = {(void*)&a};
