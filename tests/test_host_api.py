@@ -195,3 +195,33 @@ def test_sampling_statistics():
     assert abs(counts['000'] / 2000 - 0.5) < 0.05
     _, cx = circ.sample(500, orientation=[0, 0, 0], _tqdm_disable=True)   # X basis: even parity only
     assert all(k.count('1') % 2 == 0 for k in cx)
+
+
+def test_cz_pair_fusion_matches_one_split_per_gate(monkeypatch):
+    """complex64 realNoise: the two tomography CZs of an rzz are applied as one merge-and-split with the composite
+    16 x 16 Kraus tensor (Circuit._fuse_pairs). Same state as one split per gate up to the skipped intermediate
+    rank rule (e * 1e-8 absolute), far inside the complex64 tolerance; complex128 circuits never fuse."""
+    n = 4
+    files = {'CZ': {f'{i}{i + 1}': os.path.join(CHI_DIR, 'czDefault.mat') for i in range(n - 1)}, 'CP': {}}
+    kw = dict(ideal=False, noiseType='realNoise', chiFileDict=files, chi=8, kappa=3, chip='best')
+
+    def run(dtype):
+        c = Simulator.TensorCircuit(qn=n, dtype=dtype, device='cpu', **kw)
+        program(c, n, 2, 5, entangler='rzz', ghz=False, trunc_after_1q=False)
+        calls = []
+        eng = c._engine()
+        orig = eng.split_2q
+        monkeypatch.setattr(eng, 'split_2q', lambda *a, **k: (calls.append(a[2].shape[-1]), orig(*a, **k))[1])
+        c.evolve(Simulator.Tools.create_ket0Series(n, dtype=dtype, device='cpu'))
+        monkeypatch.setattr(eng, 'split_2q', orig)
+        return c.cal_dm(), calls
+
+    rho_f, calls_f = run(C64)
+    assert calls_f and all(k == 256 for k in calls_f)            # 3 rzz -> 3 fused splits
+    monkeypatch.setenv('MPDO_NO_FUSE', '1')
+    rho_s, calls_s = run(C64)
+    assert len(calls_s) == 2 * len(calls_f) and all(k == 16 for k in calls_s)
+    assert rel(rho_f, rho_s) < 2e-5
+    monkeypatch.delenv('MPDO_NO_FUSE')
+    _, calls_128 = run(C128)
+    assert all(k == 16 for k in calls_128)

@@ -9,6 +9,7 @@ single-qubit gates carry none; the rank of a gate split follows ||s|| - ||s[:k]|
 Extensions: gate angles may be 1-D tensors (B circuits evolved as one batch), non-neighbouring two-qubit
 gates are rejected up front (the reference accepts them and then breaks in truncate), and
 cal_dm(reduced_index=[...]) really traces those qubits (the reference call raises)."""
+import os
 from typing import Any, Dict, List, Optional, Tuple, Union
 
 import torch as tc
@@ -131,12 +132,77 @@ class TensorCircuit(QuantumCircuit):
             B = max(_qNodes[lo].data.shape[0], _qNodes[hi].data.shape[0])
             self._match_batch(_qNodes[lo], B)
             self._match_batch(_qNodes[hi], B)
+        self._merge_split(_qNodes, lo, hi, G, noisy)
+
+    def _merge_split(self, _qNodes: List[DenseNode], lo: int, hi: int, G: tc.Tensor, noisy: bool):
+        """Theta = T_lo . T_hi . G, split back with the reference rank rule; the noise index goes to `hi`."""
         eng = self._engine()
         _qNodes[lo].data, _qNodes[hi].data = eng.split_2q(_qNodes[lo].data, _qNodes[hi].data, G, GLOBAL_MINIMUM)
         _qNodes[lo].has_right = True
         _qNodes[hi].has_left = True
         if noisy:
             _qNodes[hi].has_inner = True
+
+    # Largest composite Kraus count a fused pair may carry (two tomography CZs: 16 x 16).
+    FUSE_MAX_K = 256
+
+    def _fuse_pairs(self, chain: list) -> list:
+        """Fuses `2q gate A ; noiseless 1q gates on the same two qubits ; 2q gate B` (same pair, no truncate in
+        between - e.g. the two CZEXP of a realNoise rzz/cx decomposition, AbstractCircuit.py:210-232) into ONE
+        merge-and-split with the composite Kraus tensor
+            G[p0,p1,s0,s1,(gB,gA)] = sum B[p0,p1,t0,t1,gB] M0[t0,u0] M1[t1,u1] A[u0,u1,s0,s1,gA].
+        The two-site tensor after gate B is the same either way; what is skipped is the reference's intermediate
+        SVD split, whose only effect on the state is its rank rule (a tail of norm <= e*1e-8 dropped, Circuit.py:120-124
+        -> decompositions.py:120-134). That is below the complex64 tolerance (1e-5) and of the size of the rule's own
+        sensitivity to fp32 rounding, so complex64 circuits fuse; complex128 circuits, circuits with a relative
+        truncation error, and MPDO_NO_FUSE=1 keep one split per gate. Entries of the returned list are either the
+        original (index, gate, oqs) tuples or ('fused', lo, hi, G, noisy)."""
+        if (self.dtype != tc.complex64 or self.max_truncation_err is not None or not self.realNoise
+                or os.environ.get('MPDO_NO_FUSE')):
+            return chain
+
+        def is_2q(op):
+            return isinstance(op[1], QuantumGate) and not op[1].single and len(op[2]) == 2
+
+        out, i = [], 0
+        while i < len(chain):
+            op = chain[i]
+            if not is_2q(op) or abs(op[2][0] - op[2][1]) != 1:
+                out.append(op)
+                i += 1
+                continue
+            lo, hi = min(op[2]), max(op[2])
+            j, mids = i + 1, []
+            while j < len(chain):
+                g, oqs = chain[j][1], chain[j][2]
+                if (isinstance(g, QuantumGate) and g.single and g.name != 'MeasureZ' and set(oqs) <= {lo, hi}
+                        and not ((self.idealNoise or self.unified) and not g.ideal)):
+                    mids.append(chain[j])
+                    j += 1
+                else:
+                    break
+            if j >= len(chain) or not is_2q(chain[j]) or {min(chain[j][2]), max(chain[j][2])} != {lo, hi}:
+                out.append(op)
+                i += 1
+                continue
+            A, noisyA = self._double_operand(op[1], op[2])
+            Bt, noisyB = self._double_operand(chain[j][1], chain[j][2])
+            if A.shape[-1] * Bt.shape[-1] > self.FUSE_MAX_K:
+                out.append(op)
+                i += 1
+                continue
+            eye = tc.eye(2, dtype=tc.complex128).reshape(1, 2, 2)
+            M = {lo: eye, hi: eye}
+            for _, g, oqs in mids:
+                U = self._single_operand(g)[0].to(tc.complex128)[..., 0]      # [Bg, 2, 2] (p, s)
+                for q in oqs:
+                    M[q] = U @ M[q]
+            tot = tc.einsum('bpqtvg, btu, bvw, buwxyh -> bpqxygh', Bt.to(tc.complex128), M[lo], M[hi],
+                            A.to(tc.complex128))
+            tot = tot.reshape(*tot.shape[:5], -1)
+            out.append(('fused', lo, hi, tot, noisyA or noisyB))
+            i = j + 1
+        return out
 
     def _apply_single_qubit_gate(self, _qNodes: List[DenseNode], _qubits, gate: QuantumGate,
                                  _oqs: Union[int, List[int]]):
@@ -240,8 +306,20 @@ class TensorCircuit(QuantumCircuit):
                 if parallel:
                     for q in {q for _, _, oqs in chain for q in oqs}:
                         adopt(state[q].data)
-                for i, g, oqs in chain:
-                    self._add_gate(state, i, _oqs=oqs, _gate=g)
+                for op in self._fuse_pairs(chain):
+                    if op[0] == 'fused':
+                        _, lo, hi, G, noisy = op
+                        G = self._dev(G)
+                        for q in (lo, hi):
+                            self._match_batch(state[q], G.shape[0])
+                        if state[lo].data.shape[0] != state[hi].data.shape[0]:
+                            B = max(state[lo].data.shape[0], state[hi].data.shape[0])
+                            self._match_batch(state[lo], B)
+                            self._match_batch(state[hi], B)
+                        self._merge_split(state, lo, hi, G, noisy)
+                    else:
+                        i, g, oqs = op
+                        self._add_gate(state, i, _oqs=oqs, _gate=g)
             return task
 
         parallel = getattr(_engine.get_prims(), 'name', '') == 'cuda' and len(strands) > 1

@@ -28,6 +28,7 @@ def _pool():
 
 
 PREWARM_SMALL_MB = int(os.environ.get('MPDO_STRAND_PREWARM_MB', '48'))   # per stream; 0 disables
+PREWARM_LARGE_MB = int(os.environ.get('MPDO_STRAND_PREWARM_LARGE_MB', '2048'))   # per stream, one splittable block
 
 
 def _prewarm(device, stream):
@@ -37,11 +38,19 @@ def _prewarm(device, stream):
     kernels of other strands are running was measured to stall every launching thread for 50-400 ms
     (tools/prof_outliers.py: the occasional 2-3x slower step). A few dozen MB of cached segments per stream make
     that path cold in steady state."""
-    if PREWARM_SMALL_MB <= 0:
-        return
     with torch.cuda.device(device), torch.cuda.stream(stream):
-        blocks = [torch.empty(1 << 20, dtype=torch.uint8, device=device) for _ in range(PREWARM_SMALL_MB)]
-        del blocks
+        if PREWARM_SMALL_MB > 0:
+            blocks = [torch.empty(1 << 20, dtype=torch.uint8, device=device) for _ in range(PREWARM_SMALL_MB)]
+            del blocks
+        # The same holds for the large pool (site tensors and gate-split outputs, up to 537 MB each on the headline
+        # workload): one big cached block per stream, which the allocator splits on demand, instead of segments
+        # that appear one cudaMalloc at a time for hundreds of steps. Capped at 1/64 of the free device memory.
+        if PREWARM_LARGE_MB > 0:
+            free_b, _ = torch.cuda.mem_get_info(device)
+            want = min(PREWARM_LARGE_MB << 20, free_b // 64)
+            if want >= (64 << 20):
+                big = torch.empty(want, dtype=torch.uint8, device=device)
+                del big
 
 
 def _streams(device, count):
