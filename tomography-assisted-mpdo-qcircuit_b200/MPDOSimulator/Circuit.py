@@ -148,7 +148,7 @@ class TensorCircuit(QuantumCircuit):
 
     def _fuse_pairs(self, chain: list) -> list:
         """Fuses `2q gate A ; noiseless 1q gates on the same two qubits ; 2q gate B` (same pair, no truncate in
-        between - e.g. the two CZEXP of a realNoise rzz/cx decomposition, AbstractCircuit.py:210-232) into ONE
+        between - e.g. the two CZEXP of a realNoise rzz decomposition, reference AbstractCircuit.py:263-275) into ONE
         merge-and-split with the composite Kraus tensor
             G[p0,p1,s0,s1,(gB,gA)] = sum B[p0,p1,t0,t1,gB] M0[t0,u0] M1[t1,u1] A[u0,u1,s0,s1,gA].
         The two-site tensor after gate B is the same either way; what is skipped is the reference's intermediate

@@ -669,7 +669,9 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
     // blocks spread one decomposition over many SMs (measured: b = 32 uses 2 SMs at 150 us per round for n = 128).
     // A full batch already fills the GPU and prefers fewer, longer rounds.
     const long long ctasAt8 = (long long)batch * ((n + 15) / 16);
-    int target = ctasAt8 <= 8 * 148 ? 16 : 32;   // (8 / 16 / 32 measured within noise on cfg2 and cfg3)
+    // Few matrices in flight: 8-row blocks with a full warp per pair (measured on graded full-rank Gram matrices,
+    // preconditioned route: n = 256 6.67 -> 5.19 ms, n = 512 19.2 -> 16.0 ms against 16-row blocks).
+    int target = ctasAt8 <= 8 * 148 ? 8 : 32;
     if (const char* e = getenv("MPDO_JACOBI_B")) target = atoi(e) > 0 ? atoi(e) : target;   // tuning knob
     if (b > target) b = target;
   }
@@ -693,7 +695,9 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
   a.rankStride = rankStride;
   const size_t smem = (size_t)(2 * b) * rowBytes;
   // lanes per row pair: short rows share a warp between several pairs (see rotate_pair)
-  int G = mt >= 384 ? 32 : 16;   // (8 / 16 / 32 measured on n = 24, 48, 96: 16 is best or equal up to mt = 192)
+  // (8 / 16 / 32 measured on single-CTA n = 24, 48, 96: 16 is best or equal up to mt = 192; multi-CTA tournaments
+  // with 8-row blocks need the full warp per pair to keep 8 warps on the SM)
+  int G = (mt >= 384 || (b < half && b <= 8)) ? 32 : 16;
   if (const char* e = getenv("MPDO_JACOBI_G")) G = atoi(e) == 8 ? 8 : (atoi(e) == 16 ? 16 : 32);   // tuning knob
   const int ppw = 32 / G;
   const unsigned threads = 32u * (unsigned)((b + ppw - 1) / ppw);
