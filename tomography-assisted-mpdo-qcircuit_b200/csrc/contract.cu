@@ -329,7 +329,10 @@ static int launch_contract(const mpdo_contract_desc& d, const void* A, const voi
     const double mnk = (double)d.M * d.N * d.K * d.batch;
     const double byts = (double)d.batch * ((double)d.M * d.K * sizeof(TA) + (double)d.K * d.N * sizeof(TB) +
                                            (double)d.M * d.N * sizeof(TC));
-    TimedLaunch timed(0, 8.0 * mnk, byts, st);   // algorithmic cost of a complex contraction
+    // algorithmic cost of a complex contraction; a Hermitian result needs its M (M + 1) / 2 entries on
+    // and below the diagonal only
+    const double flops = d.hermitian ? 4.0 * mnk * (d.M + 1.0) / d.M : 8.0 * mnk;
+    TimedLaunch timed(0, flops, byts, st);
     contract_kernel<TA, TB, TC, R, MMA><<<(unsigned)grid, threads_of(MMA), 0, st>>>(d, (const TA*)A, (const TB*)B, (TC*)C, tilesM,
                                                                     tilesN, kChunk);
   }
