@@ -182,11 +182,12 @@ int mpdo_split_2q(int dtype, int npass, int B, int l, int a0, int m, const void*
 /* Elementwise dtype conversion between complex64 and complex128 (count complex elements). */
 int mpdo_cast(int dtypeIn, int dtypeOut, int64_t count, const void* in, void* out, void* stream);
 
-/* Optional per-launch timing for the roofline leg of bench.py: while enabled, every contraction (class 0) and Jacobi
- * (class 1) launch is bracketed by CUDA events on its own stream. mpdo_timing_enable(on) clears earlier records.
+/* Optional per-launch timing for the roofline leg of bench.py: while enabled, every contraction (class 0: fp32
+ * accumulation, class 3: fp64 accumulation), Jacobi (class 1) and pivoted-Cholesky (class 2) launch is bracketed by CUDA
+ * events on its own stream. mpdo_timing_enable(on) clears earlier records.
  * mpdo_timing_summary (SYNC) sums, over the recorded launches of one class with at least minFlops algorithmic flops:
- * device seconds, algorithmic flops (8*M*N*K per complex contraction) and bytes, the launch count, and the duration /
- * flops of the largest launch. */
+ * device seconds, algorithmic flops (8*M*N*K per complex contraction, 4*(M+1)*N*K for a Hermitian result) and bytes,
+ * the launch count, and the duration / flops of the largest launch. */
 int mpdo_timing_enable(int on);
 int mpdo_timing_summary(int cls, double minFlops, double* seconds, double* flops, double* bytes, int64_t* launches,
                         double* maxFlopsSeconds, double* maxFlops);

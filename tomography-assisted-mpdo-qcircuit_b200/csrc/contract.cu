@@ -22,6 +22,8 @@
 // the same fp64 units as DFMA, so the gain is small (see the dispatch in mpdo_contract for the measured numbers).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace mpdo {
@@ -332,7 +334,7 @@ static int launch_contract(const mpdo_contract_desc& d, const void* A, const voi
     // algorithmic cost of a complex contraction; a Hermitian result needs its M (M + 1) / 2 entries on
     // and below the diagonal only
     const double flops = d.hermitian ? 4.0 * mnk * (d.M + 1.0) / d.M : 8.0 * mnk;
-    TimedLaunch timed(0, flops, byts, st);
+    TimedLaunch timed(std::is_same<R, double>::value ? 3 : 0, flops, byts, st);   // class 3: fp64 accumulation
     contract_kernel<TA, TB, TC, R, MMA><<<(unsigned)grid, threads_of(MMA), 0, st>>>(d, (const TA*)A, (const TB*)B, (TC*)C, tilesM,
                                                                     tilesN, kChunk);
   }
