@@ -225,3 +225,33 @@ def test_cz_pair_fusion_matches_one_split_per_gate(monkeypatch):
     monkeypatch.delenv('MPDO_NO_FUSE')
     _, calls_128 = run(C128)
     assert all(k == 16 for k in calls_128)
+
+
+def test_cz_pair_fusion_with_batched_angles():
+    """A parameter sweep through fused pairs: the rz angle between the two CZs of an rzz differs per circuit, so the
+    composite Kraus tensor carries the batch axis. Every circuit of the batch equals its own single run."""
+    n, B = 3, 2
+    files = {'CZ': {f'{i}{i + 1}': os.path.join(CHI_DIR, 'czDefault.mat') for i in range(n - 1)}, 'CP': {}}
+    kw = dict(qn=n, ideal=False, noiseType='realNoise', chiFileDict=files, chi=8, kappa=3, chip='best', dtype=C64,
+              device='cpu')
+    g = torch.Generator().manual_seed(11)
+    theta = torch.rand(n - 1, B, generator=g, dtype=torch.float64) * 2 * math.pi
+    u3 = (torch.rand(n, 3, generator=g, dtype=torch.float64) * 2 * math.pi).tolist()
+
+    def prog(c, th):
+        for q in range(n):
+            c.u3(*u3[q], [q])
+        for q in range(n - 1):
+            c.rzz(th[q], q, q + 1)
+            c.truncate()
+
+    batched = Simulator.TensorCircuit(**kw)
+    prog(batched, [theta[q].clone() for q in range(n - 1)])
+    batched.evolve(Simulator.Tools.create_ket0Series(n, dtype=C64))
+    rho_b = batched.cal_dm()
+    assert rho_b.shape == (B, 2 ** n, 2 ** n)
+    for b in range(B):
+        single = Simulator.TensorCircuit(**kw)
+        prog(single, [float(theta[q, b]) for q in range(n - 1)])
+        single.evolve(Simulator.Tools.create_ket0Series(n, dtype=C64))
+        assert rel(rho_b[b], single.cal_dm()) < 2e-5
