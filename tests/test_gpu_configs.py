@@ -114,3 +114,40 @@ def test_batched_sweep_is_deterministic_and_matches_singles(cuda_prims):
     for i in ids:
         single = run([i])
         assert (a[i] - single[0]).abs().max().item() < 1e-10
+
+
+def test_cfg2_full_width_fused_pairs_match_one_split_per_gate(monkeypatch):
+    """cfg2 at its full width and truncation parameters (20 qubits, chi 64, kappa 4, czDefault chi-matrix channel on
+    every bond), first nine layers (the middle bonds reach chi): the fused CZ pairs of the complex64 path and one split
+    per gate (MPDO_NO_FUSE=1), both measured against the complex128 evolution of the same circuit (never fused, fp64
+    throughout) on gauge-invariant outputs. At this size the chi / kappa cuts run through clusters of nearly equal
+    singular values, so fp32-level perturbations are amplified by the truncations; the complex64-vs-complex128 gap
+    of the gate-by-gate path is that floor (same convention as `compare` above), and the fused path must stay within
+    3 x of it."""
+    n, depth = 20, 9
+    files = {'CZ': {f'{i}{i + 1}': bc.chi_file() for i in range(n - 1)}, 'CP': {}}
+
+    def run(dtype):
+        c = Simulator.TensorCircuit(qn=n, ideal=False, noiseType='realNoise', chiFileDict=files, chi=64, kappa=4,
+                                    chip='best', dtype=dtype, device='cuda:0')
+        bc.brickwork(c, n, depth, bc.angles([0], bc.n_draws(n, depth, 'rzz')), 'rzz', trunc_after_1q=False)
+        c.evolve(Simulator.Tools.create_ket0Series(n, dtype=dtype, device='cpu'))
+        dmn = c.cal_dmNodes()
+        tr = dmOperations.trace_rho(dmn).item()
+        z = np.array([dmOperations.pauli_expect(dmn, 2, q).item() for q in range(n)])
+        zz = np.array([dmOperations.pauli_expect(dmn, [2, 2], [q, q + 1]).item() for q in range(0, n - 1, 3)])
+        bonds = [int(s.data.shape[4]) for s in c.stateNodes[:-1]]
+        return np.concatenate([[tr], z, zz]), bonds
+
+    fused, bonds_f = run(C64)
+    monkeypatch.setenv('MPDO_NO_FUSE', '1')
+    split, bonds_s = run(C64)
+    exact, _ = run(C128)
+    assert max(bonds_f) <= 64 and max(bonds_s) <= 64
+    assert 0 < exact[0] < 1                              # the tomography channel is not trace preserving
+    scale = abs(exact[0])
+    err_fused = np.abs(fused - exact).max() / scale
+    err_split = np.abs(split - exact).max() / scale
+    print(f'bonds {bonds_f}; vs complex128: fused {err_fused:.2e}, one split per gate {err_split:.2e}, '
+          f'fused vs split {np.abs(fused - split).max() / scale:.2e}')
+    assert err_fused <= max(2e-5, 3 * err_split)
