@@ -225,7 +225,7 @@ class OracleCircuit:
     """Dense restatement of TensorCircuit (Circuit.py) + QuantumCircuit builders (AbstractCircuit.py)."""
 
     def __init__(self, qn, ideal=True, noiseType='no', chiFileDict=None, chi=None, kappa=None,
-                 max_truncation_err=None, chip=None, dtype=torch.complex64, svd_mode='exact'):
+                 max_truncation_err=None, chip=None, dtype=torch.complex64, svd_mode='exact', fast=False):
         self.qn, self.ideal, self.noiseType = qn, ideal, noiseType.lower()
         self.chi, self.kappa, self.max_truncation_err = chi, kappa, max_truncation_err
         self.dtype, self.svd_mode = dtype, svd_mode
@@ -250,7 +250,10 @@ class OracleCircuit:
         self.T = None
         self.bond = None
         self.inner = None
-        self.stats = {'updates_2q_noisy': 0}
+        self.stats = {'updates_2q_noisy': 0, 'split_ranks': []}
+        # fast=True: same mathematics, smaller LAPACK calls (see _apply_2q_fast / _svd_right2left_fast); only
+        # meaningful with svd_mode='exact'. tests/test_oracle_fast.py pins it to the plain restatement.
+        self.fast = bool(fast) and svd_mode == 'exact'
 
     # ---- builders (AbstractCircuit.py:156-532), subset used by the parity suites ----
     def _add(self, name, params, oqs, ideal):
@@ -351,6 +354,8 @@ class OracleCircuit:
 
     def _apply_2q(self, name, G, var, ideal, oqs):
         """Circuit.py:74-136. The noise index goes to the higher-numbered qubit (:88-89)."""
+        if self.fast:
+            return self._apply_2q_fast(name, G, var, ideal, oqs)
         lo, hi = min(oqs), max(oqs)
         if hi != lo + 1:
             raise NotImplementedError('oracle: two-qubit gates must act on neighbouring qubits')
@@ -375,6 +380,72 @@ class OracleCircuit:
         self.T[lo] = u * sq
         self.T[hi] = sq.reshape(-1, 1, 1, 1) * vh
         self.bond[lo] = True
+        self.stats['split_ranks'].append(int(s.numel()))
+        if K > 1 or g_noise:
+            self.inner[hi] = True
+        if g_noise:
+            self.stats['updates_2q_noisy'] += 1
+
+    def _gate_operand_2q(self, name, G, var, ideal, oqs):
+        """The operand part of _apply_2q (Circuit.py:84-99): [p_lo,p_hi,s_lo,s_hi,g] and the noise flag."""
+        lo = min(oqs)
+        g_noise = (self.idealNoise and not ideal) or self.realNoise
+        if g_noise and not self.realNoise:
+            if var:
+                raise ValueError('variational two-qubit gates cannot carry idealNoise in the reference')
+            G = self.noise_cache.setdefault(name, torch.einsum('ijklp, klmn -> ijmnp', self.noise['dpc2'], G))
+        if self.realNoise and G.dim() != 5:
+            raise ValueError('realNoise mode needs a 5-index two-qubit gate tensor (CZEXP / CPEXP)')
+        if G.dim() == 4:
+            G = G.unsqueeze(-1)
+        if oqs[0] != lo:
+            G = G.permute(1, 0, 3, 2, 4)
+        return G, g_noise
+
+    def _apply_2q_fast(self, name, G, var, ideal, oqs):
+        """Circuit.py:74-136 with the (l*2*a0) x (2*a1*K*r) two-site matrix never formed: Theta =
+        (Q1 x 1) . C . (1 x Q2h) with Q1, Q2h the LAPACK QR / LQ isometries of T_lo[(l,a0),(s0,m)] and
+        T_hi[(m,s1),(a1,r)], so Theta and the core C [(x,p0),(p1,g,y)] have the same singular values and
+        SVD(Theta) = (Q1 x 1) SVD(C) (1 x Q2h). Same full LAPACK SVD, same rank rule, on the small matrix."""
+        lo, hi = min(oqs), max(oqs)
+        if hi != lo + 1:
+            raise NotImplementedError('oracle: two-qubit gates must act on neighbouring qubits')
+        G, g_noise = self._gate_operand_2q(name, G, var, ideal, oqs)
+        Tl, Th = self.T[lo], self.T[hi]
+        l, _, a0, m = Tl.shape
+        _, _, a1, r = Th.shape
+        K = G.shape[-1]
+        X = Tl.permute(0, 2, 1, 3).reshape(l * a0, 2 * m)
+        if l * a0 > 2 * m:
+            Q1, R1 = torch.linalg.qr(X)                       # [(l,a0),x], [x,(s0,m)]
+        else:
+            Q1, R1 = None, X
+        x = R1.shape[0]
+        Y = Th.reshape(m * 2, a1 * r)
+        if a1 * r > 2 * m:
+            Q2, R2 = torch.linalg.qr(Y.mH)                    # Y^h = Q2 R2  ->  Y = R2^h Q2^h
+            L2, Q2h = R2.mH, Q2.mH                            # [(m,s1),y], [y,(a1,r)]
+        else:
+            L2, Q2h = Y, None
+        y = L2.shape[1]
+        C = torch.einsum('xam,mby,PQabg->xPQgy', R1.reshape(x, 2, m), L2.reshape(m, 2, y), G)
+        u, s, vh, _ = svd(C, 2, None, GLOBAL_MINIMUM, False, mode='exact')
+        sq = torch.sqrt(s)
+        k = s.numel()
+        u = u * sq                                            # [x,P,k]
+        vh = sq.reshape(-1, 1, 1, 1) * vh                     # [k,Q,g,y]
+        if Q1 is not None:
+            Tl_n = (Q1 @ u.reshape(x, 2 * k)).reshape(l, a0, 2, k).permute(0, 2, 1, 3)
+        else:
+            Tl_n = u.reshape(l, a0, 2, k).permute(0, 2, 1, 3)
+        if Q2h is not None:
+            Th_n = (vh.reshape(k * 2 * K, y) @ Q2h).reshape(k, 2, K, a1, r)
+        else:
+            Th_n = vh.reshape(k, 2, K, a1, r)
+        self.T[lo] = Tl_n.contiguous()
+        self.T[hi] = Th_n.permute(0, 1, 3, 2, 4).reshape(k, 2, a1 * K, r).contiguous()   # inner = (a1, g) as in _apply_2q
+        self.bond[lo] = True
+        self.stats['split_ranks'].append(int(k))
         if K > 1 or g_noise:
             self.inner[hi] = True
         if g_noise:
@@ -393,11 +464,26 @@ class OracleCircuit:
 
     def _svd_right2left(self):
         """TNNOptimizer.py:111-134 (tn.split_node puts sqrt(S) on both sides)."""
+        if self.fast:
+            return self._svd_right2left_fast()
         for i in range(self.qn - 1, 0, -1):
             theta = torch.tensordot(self.T[i - 1], self.T[i], dims=([3], [0]))
             u, s, vh, rest = svd(theta, 3, self.chi, self.max_truncation_err, True, mode=self.svd_mode)
             sq = torch.sqrt(s)
             self.T[i - 1] = u * sq
+            self.T[i] = sq.reshape(-1, 1, 1, 1) * vh
+            self.stats.setdefault('discarded', []).append(rest)
+
+    def _svd_right2left_fast(self):
+        """TNNOptimizer.py:111-134 right after :87-108: the left neighbour T_{i-1} is the Q of a LAPACK QR
+        (an isometry over its right bond), so SVD(T_{i-1} . X) = T_{i-1} . SVD(X) with X = T_i as
+        [l | (s,a,r)]: the same singular values, the same rank decision, the same sqrt(S) | sqrt(S) split,
+        without forming the (l's'a') x (s a r) two-site matrix."""
+        for i in range(self.qn - 1, 0, -1):
+            X = self.T[i]
+            u, s, vh, rest = svd(X, 1, self.chi, self.max_truncation_err, True, mode='exact')
+            sq = torch.sqrt(s)
+            self.T[i - 1] = torch.tensordot(self.T[i - 1], u * sq, dims=([3], [0]))
             self.T[i] = sq.reshape(-1, 1, 1, 1) * vh
             self.stats.setdefault('discarded', []).append(rest)
 

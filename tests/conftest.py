@@ -14,6 +14,17 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
 
 
+def pytest_collection_modifyitems(config, items):
+    """Everything marked `gpu` is skipped (not errored) on a machine without a CUDA device."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason='no CUDA device')
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope='session')
 def cuda_prims():
     import torch

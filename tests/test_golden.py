@@ -191,9 +191,9 @@ def test_oracle_matches_reference(name, tag):
 
 @pytest.fixture
 def cpu_model_prims():
-    _engine._TEST_PRIMS = CpuPrims()
+    _engine._PRIMS = CpuPrims()   # CPU model of the device primitives, injected by the test
     yield
-    _engine._TEST_PRIMS = None
+    _engine._PRIMS = None
 
 
 @pytest.mark.parametrize('name', sorted(CIRCUITS))

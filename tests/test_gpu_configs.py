@@ -116,7 +116,7 @@ def test_batched_sweep_is_deterministic_and_matches_singles(cuda_prims):
         assert (a[i] - single[0]).abs().max().item() < 1e-10
 
 
-def test_cfg2_full_width_fused_pairs_match_one_split_per_gate(monkeypatch):
+def test_cfg2_full_width_fused_pairs_match_one_split_per_gate(cuda_prims, monkeypatch):
     """cfg2 at its full width and truncation parameters (20 qubits, chi 64, kappa 4, czDefault chi-matrix channel on
     every bond), first nine layers (the middle bonds reach chi): the fused CZ pairs of the complex64 path and one split
     per gate (MPDO_NO_FUSE=1), both measured against the complex128 evolution of the same circuit (never fused, fp64

@@ -35,11 +35,11 @@ def rel(a, b):
 
 
 @pytest.fixture(scope='module')
-def engines():
+def engines(cuda_prims):
     from MPDOSimulator._engine.native import NativeEngine
     from MPDOSimulator._engine.prims import CudaPrims
     from MPDOSimulator._engine.steps import Engine
-    p = CudaPrims()
+    p = cuda_prims
     return {dt: (Engine(p, dt), NativeEngine(p, dt)) for dt in (C64, C128)}
 
 

@@ -19,9 +19,9 @@ CHI_DIR = os.path.join(os.path.dirname(Simulator.__file__), 'chi')
 
 @pytest.fixture(autouse=True)
 def cpu_model_prims():
-    _engine._TEST_PRIMS = CpuPrims()
+    _engine._PRIMS = CpuPrims()   # CPU model of the device primitives, injected by the test
     yield
-    _engine._TEST_PRIMS = None
+    _engine._PRIMS = None
 
 
 def program(c, n, depth, seed, entangler='cz', ghz=True, trunc_after_1q=True):

@@ -25,7 +25,7 @@ def readout_row(circuit_id):
     import MPDOSimulator as Simulator
     from MPDOSimulator import _engine, dmOperations
     from cpu_prims import CpuPrims
-    _engine._TEST_PRIMS = CpuPrims()
+    _engine._PRIMS = CpuPrims()   # CPU model of the device primitives, injected by the test
     g = torch.Generator().manual_seed(1234 + circuit_id)
     c = Simulator.TensorCircuit(qn=NQ, ideal=False, noiseType='idealNoise', chi=4, kappa=2, chip='medium',
                                 dtype=torch.complex128, device='cpu')

@@ -116,7 +116,8 @@ class TensorCircuit(QuantumCircuit):
     # ------------------------------------------------------------------------------------------------
     # gate absorption
     # ------------------------------------------------------------------------------------------------
-    def _apply_two_qubits_gate(self, _qNodes: List[DenseNode], _qubits, gate: QuantumGate, _oqs: List[int]):
+    def _apply_two_qubits_gate(self, _qNodes: List[DenseNode], _qubits, gate: QuantumGate, _oqs: List[int],
+                               _tag=None):
         """Merge both sites with the (noisy) gate and split back by SVD (reference :74-136)."""
         if len(_oqs) != 2 or _oqs[0] == _oqs[1]:
             raise ValueError('Invalid operating qubits for a two-qubit gate.')
@@ -132,12 +133,15 @@ class TensorCircuit(QuantumCircuit):
             B = max(_qNodes[lo].data.shape[0], _qNodes[hi].data.shape[0])
             self._match_batch(_qNodes[lo], B)
             self._match_batch(_qNodes[hi], B)
-        self._merge_split(_qNodes, lo, hi, G, noisy)
+        self._merge_split(_qNodes, lo, hi, G, noisy, _tag)
 
-    def _merge_split(self, _qNodes: List[DenseNode], lo: int, hi: int, G: tc.Tensor, noisy: bool):
-        """Theta = T_lo . T_hi . G, split back with the reference rank rule; the noise index goes to `hi`."""
+    def _merge_split(self, _qNodes: List[DenseNode], lo: int, hi: int, G: tc.Tensor, noisy: bool, _tag=None):
+        """Theta = T_lo . T_hi . G, split back with the reference rank rule; the noise index goes to `hi`.
+        The kept rank (batch maximum) is recorded in last_stats['split_ranks'][layer index]."""
         eng = self._engine()
         _qNodes[lo].data, _qNodes[hi].data = eng.split_2q(_qNodes[lo].data, _qNodes[hi].data, G, GLOBAL_MINIMUM)
+        if _tag is not None:
+            self.last_stats.setdefault('split_ranks', {})[_tag] = int(_qNodes[lo].data.shape[4])
         _qNodes[lo].has_right = True
         _qNodes[hi].has_left = True
         if noisy:
@@ -152,11 +156,14 @@ class TensorCircuit(QuantumCircuit):
         merge-and-split with the composite Kraus tensor
             G[p0,p1,s0,s1,(gB,gA)] = sum B[p0,p1,t0,t1,gB] M0[t0,u0] M1[t1,u1] A[u0,u1,s0,s1,gA].
         The two-site tensor after gate B is the same either way; what is skipped is the reference's intermediate
-        SVD split, whose only effect on the state is its rank rule (a tail of norm <= e*1e-8 dropped, Circuit.py:120-124
-        -> decompositions.py:120-134). That is below the complex64 tolerance (1e-5) and of the size of the rule's own
-        sensitivity to fp32 rounding, so complex64 circuits fuse; complex128 circuits, circuits with a relative
-        truncation error, and MPDO_NO_FUSE=1 keep one split per gate. Entries of the returned list are either the
-        original (index, gate, oqs) tuples or ('fused', lo, hi, G, noisy)."""
+        SVD split, i.e. one application of its rank rule ||s|| - ||s[:k]|| <= e*1e-8 (Circuit.py:120-124 ->
+        decompositions.py:120-134; NOT a bound on the tail norm: it drops tails up to sqrt(2 ||s|| e*1e-8) ~ 2e-4
+        relative) and, in complex64, one more fp32 rounding of both site tensors. This is a documented numerical
+        deviation from the reference: tests/test_gpu_big_configs.py measures the fused and the gate-by-gate path
+        against the exact oracle on the same chi = 64 circuit (both inside the complex64 fp32 floor), bench.py
+        reports both, and complex128 circuits, circuits with a relative truncation error and MPDO_NO_FUSE=1 keep
+        one split per gate. Entries of the returned list are either the
+        original (index, gate, oqs) tuples or ('fused', lo, hi, G, noisy, layer index)."""
         if (self.dtype != tc.complex64 or self.max_truncation_err is not None or not self.realNoise
                 or os.environ.get('MPDO_NO_FUSE')):
             return chain
@@ -200,7 +207,7 @@ class TensorCircuit(QuantumCircuit):
             tot = tc.einsum('bpqtvg, btu, bvw, buwxyh -> bpqxygh', Bt.to(tc.complex128), M[lo], M[hi],
                             A.to(tc.complex128))
             tot = tot.reshape(*tot.shape[:5], -1)
-            out.append(('fused', lo, hi, tot, noisyA or noisyB))
+            out.append(('fused', lo, hi, tot, noisyA or noisyB, chain[j][0]))
             i = j + 1
         return out
 
@@ -231,7 +238,7 @@ class TensorCircuit(QuantumCircuit):
         if not isinstance(gate, QuantumGate):
             raise TypeError(f'Gate must be a QuantumGate, current type is {type(gate)}.')
         if not gate.single:
-            self._apply_two_qubits_gate(_qubits, None, gate, _oqs)
+            self._apply_two_qubits_gate(_qubits, None, gate, _oqs, _tag=_layer_num)
         else:
             self._apply_single_qubit_gate(_qubits, None, gate, _oqs)
 
@@ -308,7 +315,7 @@ class TensorCircuit(QuantumCircuit):
                         adopt(state[q].data)
                 for op in self._fuse_pairs(chain):
                     if op[0] == 'fused':
-                        _, lo, hi, G, noisy = op
+                        _, lo, hi, G, noisy, tag = op
                         G = self._dev(G)
                         for q in (lo, hi):
                             self._match_batch(state[q], G.shape[0])
@@ -316,7 +323,7 @@ class TensorCircuit(QuantumCircuit):
                             B = max(state[lo].data.shape[0], state[hi].data.shape[0])
                             self._match_batch(state[lo], B)
                             self._match_batch(state[hi], B)
-                        self._merge_split(state, lo, hi, G, noisy)
+                        self._merge_split(state, lo, hi, G, noisy, tag)
                     else:
                         i, g, oqs = op
                         self._add_gate(state, i, _oqs=oqs, _gate=g)
@@ -387,37 +394,53 @@ class TensorCircuit(QuantumCircuit):
         ctx = self._nodes4samples
         L = ctx['L0']
         for j, bit in enumerate(_history):
-            L = ctx['eng'].transfer_proj(L, ctx['Ts'][j], int(bit))
+            L = self._project(L, j, int(bit))
         return self._p1_from_left(L, len(_history))
+
+    def _project(self, L, pos, bit):
+        """Left environment after measured qubit number `pos` gave `bit`, carried on through the traced
+        (unmeasured) qubits that follow it up to the next measured one."""
+        ctx = self._nodes4samples
+        eng, Ts, measured = ctx['eng'], ctx['Ts'], ctx['measured']
+        q = measured[pos]
+        L = eng.transfer_proj(L, Ts[q], bit)
+        stop = measured[pos + 1] if pos + 1 < len(measured) else q + 1
+        for k in range(q + 1, stop):
+            L = eng.transfer(L, Ts[k])
+        return L
 
     def _p1_from_left(self, L, pos):
         ctx = self._nodes4samples
         eng, Ts, Rs = ctx['eng'], ctx['Ts'], ctx['R']
+        q = ctx['measured'][pos]
         vals = []
         for bit in (0, 1):
-            Lb = eng.transfer_proj(L, Ts[pos], bit)
-            vals.append(eng.inner(Lb, Rs[pos + 1])[0].real.item())
+            Lb = eng.transfer_proj(L, Ts[q], bit)
+            vals.append(eng.inner(Lb, Rs[q + 1])[0].real.item())
         probs = tc.tensor(vals, dtype=tc.float64) + GLOBAL_MINIMUM
         if (probs < 0).sum() > 0:
             raise RuntimeError(f"State is illegal, and your probability distribution is {probs}.")
         return (probs / probs.sum())[-1].item()
 
     def _prepare_sampling(self, nodes, measured: List[int]):
-        """Order the measured qubits first is not possible on a chain; instead trace the reduced qubits inside
-        the transfer matrices: sites not in `measured` contribute identity-traced transfer matrices."""
+        """Environments for sampling the qubits in `measured` (ascending); every other qubit is traced inside the
+        transfer-matrix chain (the reference connects its physical legs, Circuit.py:314 / dmOperations.py:18-37).
+        R[k] = trace of sites k..n-1 as [1, l, l'] (complex128); L0 = trace of the sites left of the first
+        measured qubit."""
         eng = self._engine()
         Ts_all = self._Ts(nodes)
         assert Ts_all[0].shape[0] == 1, 'sampling works on a single circuit'
         n = len(Ts_all)
-        if measured != list(range(n)):
-            raise NotImplementedError('sampling of a reduced register is listed as "next" (SURVEY 8f)')
-        # right environments R[k] = trace of sites k..n-1, as [1, l, l'] (c128)
+        if not measured or sorted(set(measured)) != list(measured) or measured[-1] >= n:
+            raise ValueError('measured qubits must be a non-empty ascending list of distinct qubit indices')
         R = [None] * (n + 1)
         R[n] = tc.ones((1, 1, 1), dtype=tc.complex128, device=Ts_all[0].device)
-        for k in range(n - 1, -1, -1):
+        for k in range(n - 1, measured[0], -1):
             R[k] = eng.transfer_right(R[k + 1], Ts_all[k])
-        self._nodes4samples = {'eng': eng, 'Ts': Ts_all, 'R': R,
-                               'L0': tc.ones((1, 1, 1), dtype=tc.complex128, device=Ts_all[0].device)}
+        L0 = tc.ones((1, 1, 1), dtype=tc.complex128, device=Ts_all[0].device)
+        for k in range(measured[0]):
+            L0 = eng.transfer(L0, Ts_all[k])
+        self._nodes4samples = {'eng': eng, 'Ts': Ts_all, 'R': R, 'L0': L0, 'measured': list(measured)}
         self._indices4samples = measured
 
     def _conditional_batch_sample(self, shots: int, _sampleLength: int, _bool: bool = False,
@@ -444,9 +467,9 @@ class TensorCircuit(QuantumCircuit):
                 sequences[start:start + k1, pos] = True if _bool else 1
                 if pos < _sampleLength - 1:
                     if k1 > 0:
-                        nxt.append((ctx['eng'].transfer_proj(L, ctx['Ts'][pos], 1), start, k1))
+                        nxt.append((self._project(L, pos, 1), start, k1))
                     if k0 > 0:
-                        nxt.append((ctx['eng'].transfer_proj(L, ctx['Ts'][pos], 0), start + k1, k0))
+                        nxt.append((self._project(L, pos, 0), start + k1, k0))
             groups = nxt
         return sequences.tolist()
 

@@ -55,6 +55,12 @@ class QuantumGate(ABC, nn.Module):
     def _check_Para_Tensor(self, *parameters):
         def convert(param):
             if isinstance(param, Tensor):
+                if param.requires_grad:
+                    # the reference's gates carry requires_grad through torch ops (e.g. ZGates.py:65-68); the CUDA
+                    # update path has no backward pass, so refuse rather than return gradient-free results
+                    raise NotImplementedError(
+                        'autograd through the CUDA update path is not implemented: gate parameters must not '
+                        'require grad (detach() them, or differentiate by parameter shift with a batched sweep)')
                 return param.detach().to(dtype=self.dtype, device='cpu')
             if isinstance(param, float):
                 return torch.tensor(param, dtype=self.dtype)

@@ -50,6 +50,7 @@ def qr_left2right(_qubits: List[DenseNode]):
         if not _qubits[i].has_right:
             raise ValueError(f'Axis name bond_{i}_{i + 1} not found')  # the reference indexes it unconditionally
         _qubits[i].data, _qubits[i + 1].data = eng.qr_step(_qubits[i].data, _qubits[i + 1].data)
+        _qubits[i]._left_canonical = _qubits[i].data      # svd_right2left relies on this isometry
 
 
 def svd_right2left(_qubits: List[DenseNode], max_singular_values: Optional[int] = None,
@@ -57,6 +58,11 @@ def svd_right2left(_qubits: List[DenseNode], max_singular_values: Optional[int] 
     """Two-site SVD truncation for idx = n-1..1, sqrt(S) on both sides (TNNOptimizer.py:111-134). The left
     neighbour is an isometry after qr_left2right, so only T_idx is decomposed (SVD(Q X) = Q SVD(X))."""
     _validate_qubit_list(_qubits, "svd_right2left")
+    # SVD(Q X) = Q SVD(X) needs every left neighbour to be the isometry qr_left2right left behind; the reference
+    # contracts both sites and is valid for any state, so a state that is not (any more) left-canonical is
+    # canonicalised here first instead of being truncated wrongly
+    if any(getattr(q, '_left_canonical', None) is not q.data for q in _qubits[:-1]):
+        qr_left2right(_qubits)
     eng = _engine_of(_qubits)
     discarded = []
     for idx in range(len(_qubits) - 1, 0, -1):

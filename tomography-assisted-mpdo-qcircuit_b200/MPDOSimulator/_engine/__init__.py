@@ -9,14 +9,11 @@ def default_prims():
 
 
 _PRIMS = None          # process-wide device back end, created on first use
-_TEST_PRIMS = None     # test hook only (tests/cpu_prims.py); never set by product code
 _ENGINES = {}
 
 
 def get_prims():
     global _PRIMS
-    if _TEST_PRIMS is not None:
-        return _TEST_PRIMS
     if _PRIMS is None:
         _PRIMS = default_prims()
     return _PRIMS
