@@ -18,9 +18,18 @@ only gathers the per-circuit readout at the end of the timed region.
            state) inside the timed region
   roofline / cpu_baseline: see DESIGN.md section 5.
 
+  value_one_split_per_gate: the same K layers with MPDO_NO_FUSE=1 (one split per chi-matrix CZ, as the reference does;
+           `value` fuses the two CZs of an rzz into one split - a documented numerical deviation)
+  cfg4   : the batched configuration of BASELINE.json (configs[3]) on every N: circuits sharded `id mod world`
+           (MPDOSimulator/_engine/sharding.py), CFG4_PER_RANK circuits per rank evolved as one batch, the 32-wide
+           readout rows (16 <Z>, 15 <ZZ>, P(0...0)) gathered with one NCCL all-gather INSIDE the timed region;
+           circuits/s device-resident and end to end (angles from pinned host memory, table back to the host)
+
 `--impl reference` times the reference's own formulation on the host cores: the oracle in reference mode
-(torch CPU, all threads) on a bounded sample of the same workload - one rzz (two chi-matrix CZ updates) on a
-steady-state three-site window plus the QR / chi-SVD / kappa-SVD steps that touch that pair.
+(torch CPU, all threads) on a bounded sample of the same workload - two rzz (four chi-matrix CZ updates) on a
+steady-state six-site window plus the QR / chi-SVD / kappa-SVD sweep of the window (5 bonds for 4 updates; the real
+layer sweeps 19 bonds for 18-20 updates). --warmup repeats run untimed first. For N > 1 the driver's per-N ratio
+divides N GPUs by this ONE CPU process.
 """
 import argparse
 import json
@@ -114,20 +123,23 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle in reference mode on a bounded sample
 # ---------------------------------------------------------------------------------------------------
-def cpu_sample(repeats=1, threads=None):
-    """One rzz (= 2 chi-matrix CZ updates) on sites (1, 2) of a four-site steady-state window with Gaussian
-    tensors (re, im ~ N(0,1)/sqrt(2 chi kappa), seed 7; SURVEY 8d micro-benchmark) followed by the truncate
-    sweep of the window, oracle in reference mode (randomized SVD branch as in decompositions.py:112-115).
-    Returns (updates, seconds per repeat list, cores)."""
+def cpu_sample(repeats=1, threads=None, window=6, warmup=0):
+    """`window` = 4: one rzz (= 2 chi-matrix CZ updates) on sites (1, 2) of a four-site steady-state window;
+    `window` = 6: rzz on (1, 2) and (3, 4) (4 updates, 5 swept bonds - the sweep-per-update ratio of the real layer
+    within 25 %). Gaussian site tensors (re, im ~ N(0,1)/sqrt(2 chi kappa), seed 7; SURVEY 8d micro-benchmark)
+    followed by the truncate sweep of the window, oracle in reference mode (randomized SVD branch as in
+    decompositions.py:112-115). Returns (updates per repeat, seconds per timed repeat, cores)."""
     from oracle.mpdo_oracle import OracleCircuit
     threads = threads or os.cpu_count()
     torch.set_num_threads(threads)
-    files = {'CZ': {'12': chi_file()}, 'CP': {}}
+    pairs = [(1, 2)] if window == 4 else [(1, 2), (3, 4)]
+    files = {'CZ': {f'{a}{b}': chi_file() for a, b in pairs}, 'CP': {}}
     times = []
-    for rep in range(repeats):
-        oc = OracleCircuit(4, ideal=False, noiseType='realNoise', chiFileDict=files, chi=CHI, kappa=KAPPA,
+    for rep in range(warmup + repeats):
+        oc = OracleCircuit(window, ideal=False, noiseType='realNoise', chiFileDict=files, chi=CHI, kappa=KAPPA,
                            chip='best', dtype=torch.complex64, svd_mode='reference')
-        oc.rzz(0.7 + 0.1 * rep, 1, 2)
+        for a, b in pairs:
+            oc.rzz(0.7 + 0.1 * rep + 0.05 * a, a, b)
         oc.truncate()
         g = torch.Generator().manual_seed(7)
         scale = 1.0 / math.sqrt(2 * CHI * KAPPA)
@@ -135,40 +147,170 @@ def cpu_sample(repeats=1, threads=None):
         def gauss(l, r):
             return torch.complex(torch.randn(l, 2, KAPPA, r, generator=g), torch.randn(l, 2, KAPPA, r, generator=g)) * scale
 
-        oc.T = [gauss(1, CHI), gauss(CHI, CHI), gauss(CHI, CHI), gauss(CHI, 1)]
-        oc.bond = [True, True, True]
-        oc.inner = [True] * 4
+        oc.T = [gauss(1, CHI)] + [gauss(CHI, CHI) for _ in range(window - 2)] + [gauss(CHI, 1)]
+        oc.bond = [True] * (window - 1)
+        oc.inner = [True] * window
         t0 = time.perf_counter()
         oc.run_layers()
-        times.append(time.perf_counter() - t0)
-    return 2, times, threads
+        if rep >= warmup:
+            times.append(time.perf_counter() - t0)
+    return 2 * len(pairs), times, threads
+
+
+CFG4 = dict(n=16, depth=16, chi=64, kappa=4)
+CFG4_PER_RANK = int(os.environ.get('MPDO_BENCH_CFG4_PER_RANK', '128'))   # = 1024 circuits / 8 GPUs
+CFG4_WORKLOAD = ('cfg4: independent 16q noisy parameter-sweep circuits (U3 + CZ brickwork depth 16, idealNoise/medium: '
+                 'amplitude damping + dephasing + 2q depolarizing), chi=64, kappa=4, complex64')
+
+
+CFG4_CPU_SAMPLE = ('oracle (reference mode) on brickwork layers 6-7 of circuit 0 (%.1f s), a circuit counted as 8 such '
+                   'layer pairs (favours the CPU: the whole circuit measured once in the build container took 171-186 s on '
+                   '8 cores = 0.0056 circuits/s, 123 s of it in the layer-1 gate split on un-truncated inner indices)')
+
+
+def cfg4_cpu_sample(threads=None):
+    """Bounded CPU sample of the batched configuration: brickwork layers 6 and 7 (one even + one odd layer: 15 noisy
+    CZ updates and 4 truncate sweeps over 16 sites) of circuit 0 in reference mode, starting from the state the
+    exact-mode oracle (fast formulation) prepared with layers 0-5. A circuit is counted as 8 such layer pairs:
+    circuits/s = 1 / (8 * t). That FAVOURS the CPU: the whole circuit measured once in the build container took
+    171-186 s on 8 cores, of which 123 s is the single layer-1 gate split on un-truncated inner indices (the reference
+    forms and decomposes the full two-site matrix there) and ~4.7 s each steady-state layer."""
+    import bench_configs as bc
+    from oracle.mpdo_oracle import OracleCircuit
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    n, depth = CFG4['n'], 8
+
+    def build(mode, fast):
+        oc = OracleCircuit(n, ideal=False, noiseType='idealNoise', chi=CFG4['chi'], kappa=CFG4['kappa'], chip='medium',
+                           dtype=torch.complex64, svd_mode=mode, fast=fast)
+        bc.brickwork(oc, n, depth, bc.angles([0], bc.n_draws(n, CFG4['depth'], 'cz')), 'cz')
+        return oc
+
+    def split_layers(oc):
+        chunks, cur, ntr = [], [], 0
+        for L in oc.layers:
+            cur.append(L)
+            if L[0] == 'truncate':
+                ntr += 1
+                if ntr % 2 == 0:
+                    chunks.append(cur)
+                    cur = []
+        return chunks
+
+    prep = build('exact', True)
+    chunks = split_layers(prep)
+    prep.layers = [L for ch in chunks[:6] for L in ch]
+    prep.evolve()
+    ref = build('reference', False)
+    ref.T, ref.bond, ref.inner = [t.clone() for t in prep.T], list(prep.bond), list(prep.inner)
+    ref.layers = [L for ch in split_layers(ref)[6:8] for L in ch]
+    t0 = time.perf_counter()
+    ref.run_layers()
+    secs = time.perf_counter() - t0
+    return secs, threads
 
 
 def reference_arm(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    for _ in range(args.warmup):
-        pass  # the sample is deterministic CPU work; warm-up repeats would only lengthen the run
-    updates, times, cores = cpu_sample(repeats=max(1, args.steps))
+    updates, times, cores = cpu_sample(repeats=max(1, args.steps), window=6, warmup=max(0, args.warmup))
     total = sum(times)
     value = updates * len(times) / total
+    upd4, times4, _ = cpu_sample(repeats=1, window=4)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'c64', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'chi': CHI, 'kappa': KAPPA},
+        'config': {'workload': WORKLOAD, 'chi': CHI, 'kappa': KAPPA,
+                   'note': 'ONE CPU process on all host cores whatever --gpus says: a per-N ratio against this line '
+                           'divides N GPUs by one CPU process'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': 'oracle (reference mode) on one rzz = 2 chi-matrix CZ updates + the truncate '
-                                   'sweep of a 4-site steady-state Gaussian window, per step'},
+                         'sample': 'oracle (reference mode) on two rzz = 4 chi-matrix CZ updates + the truncate sweep '
+                                   '(5 bonds, 6 kappa sites) of a 6-site steady-state Gaussian window, per step; '
+                                   '%d warm-up repeats untimed' % max(0, args.warmup),
+                         'four_site_window_value': upd4 / times4[0]},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
+    if not args.no_cfg4:
+        secs4, _ = cfg4_cpu_sample()
+        line['cfg4'] = {'metric': 'circuits_per_sec', 'value': 1.0 / (8 * secs4), 'unit': 'circuits/s', 'cores': cores,
+                        'kind': 'port', 'workload': CFG4_WORKLOAD,
+                        'sample': CFG4_CPU_SAMPLE % secs4}
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------------
+def cfg4_leg(dev, rank, world, barrier):
+    """BASELINE configs[3] on `world` GPUs: circuit ids 0 .. CFG4_PER_RANK*world-1 sharded `id mod world`, each rank
+    evolves its shard as ONE batch through the public API, builds the 32-wide readout rows and the ranks exchange them
+    with one all-gather (NCCL over NVLink) inside the timed region. Returns per-rank seconds; the caller takes the max."""
+    import bench_configs as bc
+    import MPDOSimulator as Simulator
+    from MPDOSimulator import dmOperations
+    from MPDOSimulator._engine.sharding import gather_readout, shard
+    n, depth = CFG4['n'], CFG4['depth']
+    total = CFG4_PER_RANK * world
+    ids = shard(range(total), rank, world)
+    ang_host = bc.angles(ids, bc.n_draws(n, depth, 'cz')).pin_memory()     # [draws, B] float64, pinned host memory
+    copied = [0]
+
+    def build(ang):
+        c = Simulator.TensorCircuit(qn=n, ideal=False, noiseType='idealNoise', chi=CFG4['chi'], kappa=CFG4['kappa'],
+                                    chip='medium', dtype=torch.complex64, device=dev)
+        bc.brickwork(c, n, depth, ang, 'cz')
+        return c
+
+    def run(c):
+        st = Simulator.Tools.create_ket0Series(n, dtype=torch.complex64, device='cpu')
+        c.evolve(st)
+        dmn = c.cal_dmNodes()
+        cols = [dmOperations.pauli_expect(dmn, 2, q) for q in range(n)]
+        cols += [dmOperations.pauli_expect(dmn, [2, 2], [q, q + 1]) for q in range(n - 1)]
+        cols.append(c._engine().chain_value_proj(c._Ts(), [0] * n))
+        rows = torch.stack([x.reshape(-1).to(torch.float64) for x in cols], dim=1)     # [B, 32]
+        return gather_readout(rows, total), c.last_stats.get('noisy_2q_updates', 0)
+
+    run(build(ang_host))                      # rehearsal of the identical workload (pools, descriptor caches, NCCL)
+    barrier()
+    # device-resident leg: circuit objects (gate operands) built before the clock starts
+    c = build(ang_host)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    table, updates = run(c)
+    e1.record()
+    barrier()
+    secs = e0.elapsed_time(e1) * 1e-3
+    # end-to-end leg: angles start in pinned host memory, circuits are built, evolved, read out, gathered and the
+    # table lands in host memory, all inside the timed region; gate operands uploaded are counted
+    orig_dev = Simulator.TensorCircuit._dev
+
+    def counting_dev(self, t):
+        out = orig_dev(self, t)
+        copied[0] += out.numel() * out.element_size()
+        return out
+
+    Simulator.TensorCircuit._dev = counting_dev
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    f0.record()
+    table2, _ = run(build(ang_host))
+    host_table = table2.cpu()
+    f1.record()
+    barrier()
+    Simulator.TensorCircuit._dev = orig_dev
+    e2e_secs = f0.elapsed_time(f1) * 1e-3
+    finite = bool(torch.isfinite(host_table).all())
+    same = float((table - table2).abs().max())
+    return {'secs': secs, 'e2e_secs': e2e_secs, 'circuits_per_rank': len(ids), 'total': total, 'updates': updates,
+            'h2d': copied[0], 'd2h': host_table.numel() * 8, 'finite': finite, 'repeat_diff': same,
+            'trace_like_p0_first': float(host_table[0, -1]), 'peak_mem_GB': torch.cuda.max_memory_allocated() / 2 ** 30}
+
+
 def b200_arm(args):
     import torch.distributed as dist
     rank = int(os.environ.get('RANK', '0'))
@@ -337,6 +479,33 @@ def b200_arm(args):
     barrier()
     e2e_secs = e0.elapsed_time(e1) * 1e-3
 
+    # ---- one split per gate: the same K layers the way the reference splits them (MPDO_NO_FUSE=1: every chi-matrix CZ
+    # of an rzz gets its own SVD split and rank rule). Rehearsed once (other ranks, other scratch shapes), then timed.
+    nofuse_secs = None
+    if not args.no_unfused:
+        os.environ['MPDO_NO_FUSE'] = '1'
+        for timed in (False, True):
+            for s, snap in zip(state, snapshot):
+                s.data = snap.clone()
+            n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            barrier()
+            n0.record()
+            for d in range(P + W, P + W + K):
+                flush.zero_()
+                circuits[d][0].evolve(state)
+            n1.record()
+            barrier()
+            if timed:
+                nofuse_secs = n0.elapsed_time(n1) * 1e-3
+        del os.environ['MPDO_NO_FUSE']
+
+    # ---- cfg4: the batched configuration, sharded over the ranks -----------------------------------------------
+    cfg4 = None
+    if not args.no_cfg4:
+        del state, snapshot, circuits
+        torch.cuda.empty_cache()
+        cfg4 = cfg4_leg(dev, rank, world, barrier)
+
     def max_over_ranks(x):
         if world == 1:
             return x
@@ -352,6 +521,10 @@ def b200_arm(args):
         return t.item()
 
     secs, e2e_secs = max_over_ranks(secs), max_over_ranks(e2e_secs)
+    if nofuse_secs is not None:
+        nofuse_secs = max_over_ranks(nofuse_secs)
+    if cfg4 is not None:
+        cfg4['secs'], cfg4['e2e_secs'] = max_over_ranks(cfg4['secs']), max_over_ranks(cfg4['e2e_secs'])
     tot_updates, tot_e2e_updates = sum_over_ranks(updates), sum_over_ranks(e2e_updates)
     tot_launches = sum_over_ranks(launches)
 
@@ -425,10 +598,10 @@ def b200_arm(args):
         }
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            upd, times, cores = cpu_sample(repeats=1)
-            cpu = {'value': upd / times[0], 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                   'sample': 'oracle (reference mode) on one rzz = 2 chi-matrix CZ updates + the truncate sweep of '
-                             'a 4-site steady-state Gaussian window (%.1f s)' % times[0]}
+            upd, times, cores = cpu_sample(repeats=3, window=6, warmup=1)
+            cpu = {'value': upd * len(times) / sum(times), 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                   'sample': 'oracle (reference mode) on two rzz = 4 chi-matrix CZ updates + the truncate sweep (5 bonds) '
+                             'of a 6-site steady-state Gaussian window, 3 repeats after 1 warm-up (%.1f s)' % sum(times)}
         line = {
             'metric': METRIC, 'value': tot_updates / secs, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
             'ms_per_step': 1e3 * secs / K, 'ms_each_step': [round(x, 2) for x in step_ms], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -448,6 +621,33 @@ def b200_arm(args):
             'gpu_launches': int(tot_launches), 'clocks': clocks, 'roofline': roof, 'factorisation_kernels': dominant,
             'cpu_baseline': cpu,
         }
+        if nofuse_secs is not None:
+            line['value_one_split_per_gate'] = {
+                'value': tot_updates / nofuse_secs, 'unit': UNIT, 'ms_per_step': 1e3 * nofuse_secs / K,
+                'note': 'same K layers with MPDO_NO_FUSE=1: one SVD split + rank rule per chi-matrix CZ as in the '
+                        'reference (Circuit.py:120-124); `value` fuses the two CZs of an rzz into one split'}
+        if cfg4 is not None:
+            cps, cps_e2e = cfg4['total'] / cfg4['secs'], cfg4['total'] / cfg4['e2e_secs']
+            line['cfg4'] = {
+                'metric': 'circuits_per_sec', 'value': cps, 'unit': 'circuits/s', 'n_gpus': world, 'scaling': 'weak',
+                'circuits_total': cfg4['total'], 'circuits_per_gpu': cfg4['circuits_per_rank'],
+                'seconds': cfg4['secs'], 'noisy_2q_updates_per_circuit': cfg4['updates'],
+                'e2e': {'value': cps_e2e, 'unit': 'circuits/s', 'seconds': cfg4['e2e_secs'],
+                        'h2d_bytes_per_step': cfg4['h2d'], 'd2h_bytes_per_step': cfg4['d2h']},
+                'config': {'workload': CFG4_WORKLOAD, 'sharding': 'circuit id mod world (_engine/sharding.py), one batch of '
+                           '%d circuits per GPU = the per-GPU share of the 1024-circuit job on 8 GPUs' % cfg4['circuits_per_rank'],
+                           'exchange': 'one all-gather of the [circuits, 32] float64 readout table (16 <Z>, 15 <ZZ>, '
+                                       'P(0...0)) inside the timed region',
+                           'warmup': 'one untimed rehearsal of the identical batch',
+                           'l2': 'the batched site tensors (537 MB per layer sweep) exceed L2'},
+                'checks': {'readout_finite': cfg4['finite'], 'repeat_max_abs_diff': cfg4['repeat_diff'],
+                           'peak_mem_GB': cfg4['peak_mem_GB']},
+            }
+            if world == 1 and not args.no_cpu_baseline:
+                secs4, cores4 = cfg4_cpu_sample()
+                line['cfg4']['cpu_baseline'] = {
+                    'value': 1.0 / (8 * secs4), 'unit': 'circuits/s', 'cores': cores4, 'kind': 'port',
+                    'sample': CFG4_CPU_SAMPLE % secs4}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -460,6 +660,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-cfg4', action='store_true', help='skip the batched (cfg4) leg')
+    ap.add_argument('--no-unfused', action='store_true', help='skip the MPDO_NO_FUSE=1 leg')
     ap.add_argument('--profile', default=None, help='write a per-kernel time table of one steady-state step here')
     args = ap.parse_args()
     if args.impl == 'reference':

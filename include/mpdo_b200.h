@@ -156,17 +156,22 @@ int mpdo_qr_step(int dtype, int npass, int B, int l, int a, int r, const void* T
                  void* Q_out, void* Tn_out, void* stream);
 
 /* One step of the right-to-left bond truncation to k = min(chi, l) singular values: Tl [B,lp,2,ap,l] (left
- * isometric), Tr [B,l,2,a,r] -> Tl.U sqrt(S) [B,lp,2,ap,k], sqrt(S) Vh [B,k,2,a,r]; sv_out (optional, [B,l] doubles)
- * receives the singular values (their squares when npass = 1).
+ * isometric), Tr [B,l,2,a,r] -> Tl.U sqrt(S) [B,lp,2,ap,k'], sqrt(S) Vh [B,k',2,a,r]; sv_out (optional, [B,l] doubles)
+ * receives the singular values (their squares when npass = 1). max_err < 0: k' = k. max_err >= 0: the reference's
+ * relative rule (decompositions.py:117-134 with relative=True: ||s|| - ||s[:k']|| <= max_err * s[0], batch maximum)
+ * lowers k' further; SYNC (rank read-back); the outputs are written densely with k' into buffers sized for k, and
+ * *k_out = k'.
  * Replaces: tn.contract_between + tn.split_node at TNNOptimizer.py:126-133 (decompositions.svd :51-146). */
 int mpdo_bond_svd_step(int dtype, int npass, int B, int lp, int ap, int l, const void* Tl, int a, int r, const void* Tr,
-                       int k, void* Tl_out, void* Tr_out, double* sv_out, void* stream);
+                       int k, double max_err, int* k_out, void* Tl_out, void* Tr_out, double* sv_out, void* stream);
 
-/* Inner-index truncation T [B,l,2,a,r] -> U.S [B,l,2,k,r], k = min(kappa, a); disc_out (optional, [B] doubles) = norm
- * of the discarded part. SYNC when the top-k subspace iteration is used (a >= 64 and a >= 8k).
+/* Inner-index truncation T [B,l,2,a,r] -> U.S [B,l,2,k',r], k = min(kappa, a) (k = a for kappa = None); max_err and
+ * k_out as above (TNNOptimizer.py:189 passes max_truncation_err with relative=True). disc_out (optional, [B] doubles)
+ * = norm of the discarded part. SYNC when the top-k subspace iteration is used (max_err < 0, a >= 64 and a >= 8k) or
+ * max_err >= 0.
  * Replaces: tn.split_node_full_svd + contract_between at TNNOptimizer.py:186-197. */
-int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const void* T, int k, void* T_out, double* disc_out,
-                        void* stream);
+int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const void* T, int k, double max_err, int* k_out,
+                        void* T_out, double* disc_out, void* stream);
 
 /* Two-qubit gate absorption and split: T_lo [B,l,2,a0,m], T_hi [B,m,2,a1,r], G [Bg,2,2,2,2,K] as
  * [p_lo,p_hi,s_lo,s_hi,g] (Bg = 1 or B, same dtype as the state) -> T_lo' [B,l,2,a0,k], T_hi' [B,k,2,K*a1,r] with the

@@ -233,6 +233,7 @@ class OracleCircuit:
         self.layers = []            # ('gate', name, tensor, single, variational, ideal, oqs) | ('truncate',) | ('barrier',)
         self.noise_cache = {}       # Circuit.py:93-96,146-151: keyed by gate name only
         self.cz_tensors = {}
+        self.cp_tensors = {}
         if not ideal:
             if self.noiseType not in ['unified', 'realnoise', 'idealnoise']:
                 raise ValueError(f'Unsupported noise type: {self.noiseType}')  # Circuit.py:54-55
@@ -247,6 +248,10 @@ class OracleCircuit:
                     if fn not in cache:
                         cache[fn] = chi_to_tensor(read_chi(fn)).to(dtype)
                     self.cz_tensors[key] = cache[fn]
+                for key, fn in files.get('CP', {}).items():                       # cpExp_channel, RealNoise.py:173-179
+                    if fn not in cache:
+                        cache[fn] = chi_to_tensor(read_chi(fn)).to(dtype)
+                    self.cp_tensors[key] = cache[fn]
         self.T = None
         self.bond = None
         self.inner = None
@@ -307,7 +312,16 @@ class OracleCircuit:
     def swap(self, q0, q1, _ideal=None): self._add('SWAP', [], [q0, q1], _ideal)
     def iswap(self, q0, q1, _ideal=None): self._add('ISWAP', [], [q0, q1], _ideal)
     def ii(self, q0, q1, _ideal=None): self._add('II', [], [q0, q1], _ideal)
-    def cp(self, theta, q0, q1, _ideal=None): self._add('CP', [theta], [q0, q1], _ideal)
+    def cp(self, theta, q0, q1, _ideal=None):                                    # AbstractCircuit.py:404-422
+        if not self.realNoise or _ideal:
+            self._add('CP', [theta], [q0, q1], _ideal)
+        else:
+            tensor = self.cp_tensors.get(f'{q0}{q1}')
+            if tensor is None:
+                tensor = self.cp_tensors.get(f'{q1}{q0}')
+            if tensor is None:
+                raise FileNotFoundError('oracle: no CP chi file for this pair (the reference default path does not exist)')
+            self.layers.append(('gate', 'CPEXP', tensor, False, False, False, [q0, q1]))
 
     def rzz(self, theta, q0, q1, _ideal=None):                                   # AbstractCircuit.py:263-275
         if not self.realNoise or _ideal:

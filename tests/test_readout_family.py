@@ -30,3 +30,19 @@ def test_gate_parameters_that_require_grad_are_refused():
     with pytest.raises(NotImplementedError):
         c.rz(theta, [0])
     c.rz(theta.detach(), [0])     # the documented way
+
+
+def test_adaptive_ranks_cpu_model():
+    import extension_cases as ec
+    ec.check_adaptive_ranks(torch.complex128, 'cpu', 1e-9)
+    ec.check_adaptive_ranks(torch.complex128, 'cpu', 1e-9, err=5e-3, chi=12, kappa=5)
+
+
+def test_long_range_gates_cpu_model():
+    import extension_cases as ec
+    ec.check_long_range_gates(torch.complex128, 'cpu', 1e-9)
+
+
+def test_chi_formats_and_cp_tomography_cpu_model(tmp_path):
+    import extension_cases as ec
+    ec.check_chi_formats_and_cp(torch.complex128, 'cpu', 1e-9, str(tmp_path))

@@ -7,7 +7,7 @@ neighbouring pair shares a bond; the noise-tensor cache is keyed by gate name; i
 variational two-qubit gate raises; in unified mode two-qubit gates carry no noise and in realNoise mode
 single-qubit gates carry none; the rank of a gate split follows ||s|| - ||s[:k]|| <= e * 1e-8.
 Extensions: gate angles may be 1-D tensors (B circuits evolved as one batch), non-neighbouring two-qubit
-gates are rejected up front (the reference accepts them and then breaks in truncate), and
+gates are routed through noiseless SWAPs (the reference accepts them and then breaks in truncate), and
 cal_dm(reduced_index=[...]) really traces those qubits (the reference call raises)."""
 import os
 from typing import Any, Dict, List, Optional, Tuple, Union
@@ -122,11 +122,26 @@ class TensorCircuit(QuantumCircuit):
         if len(_oqs) != 2 or _oqs[0] == _oqs[1]:
             raise ValueError('Invalid operating qubits for a two-qubit gate.')
         lo, hi = min(_oqs), max(_oqs)
-        if hi != lo + 1:
-            raise NotImplementedError('two-qubit gates must act on neighbouring qubits (the reference truncation '
-                                      'breaks on long bonds: TNNOptimizer.py:94-95)')
         G, noisy = self._double_operand(gate, _oqs)
         G = self._dev(G)
+        if hi != lo + 1:
+            # Non-neighbouring qubits: the reference accepts the gate but its truncate() then indexes a
+            # bond that does not exist (TNNOptimizer.py:94-95). Here the higher qubit is routed next to the lower one
+            # by noiseless SWAPs, the gate acts on (lo, lo+1), and the SWAPs are undone: the state on the register is
+            # the one the long-range gate defines, every bond is a nearest-neighbour bond, and truncate() works.
+            # The Kraus index of the gate stays on site lo+1 (it is only ever traced against its own conjugate).
+            swap = self._dev(tc.tensor([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]],
+                                       dtype=self.dtype).reshape(1, 2, 2, 2, 2, 1))
+            for k in range(hi - 1, lo, -1):
+                self._pair_op(_qNodes, k, k + 1, swap, False, None)
+            self._pair_op(_qNodes, lo, lo + 1, G, noisy, _tag)
+            for k in range(lo + 1, hi):
+                self._pair_op(_qNodes, k, k + 1, swap, False, None)
+            return
+        self._pair_op(_qNodes, lo, hi, G, noisy, _tag)
+
+    def _pair_op(self, _qNodes: List[DenseNode], lo: int, hi: int, G: tc.Tensor, noisy: bool, _tag=None):
+        """Batch bookkeeping + merge-and-split of one neighbouring pair."""
         for q in (lo, hi):
             self._match_batch(_qNodes[q], G.shape[0])
         if _qNodes[lo].data.shape[0] != _qNodes[hi].data.shape[0]:
@@ -299,7 +314,7 @@ class TensorCircuit(QuantumCircuit):
             return x
 
         for _, _, oqs in ops:
-            for q in oqs[1:]:
+            for q in range(min(oqs), max(oqs) + 1):   # a long-range gate is routed through the qubits in between
                 parent[find(q)] = find(oqs[0])
         strands = {}
         for op in ops:
@@ -308,33 +323,129 @@ class TensorCircuit(QuantumCircuit):
             if isinstance(g, QuantumGate) and not g.single and ((self.idealNoise and not g.ideal) or self.realNoise):
                 self.last_stats['noisy_2q_updates'] = self.last_stats.get('noisy_2q_updates', 0) + 1
 
-        def make(chain):
+        # Strands whose step sequences and tensor shapes coincide (the bulk brick pairs of a layer) are stacked along
+        # the batch axis and run as ONE launch sequence (the kernels' batch dimension does not care whether its
+        # entries are circuits of a sweep or brick pairs of one circuit); the handful of distinct groups that remain
+        # (chain ends) are issued concurrently, one CUDA stream each.
+        cuda = getattr(_engine.get_prims(), 'name', '') == 'cuda'
+        programs = [self._program(chain) for chain in strands.values()]
+        groups = {}
+        for prog in programs:
+            key = self._signature(state, prog) if (cuda and os.environ.get('MPDO_GROUPING', '1') != '0') else id(prog)
+            groups.setdefault(key, []).append(prog)
+        parallel = cuda and len(groups) > 1
+
+        def make(members):
             def task():
                 if parallel:
-                    for q in {q for _, _, oqs in chain for q in oqs}:
-                        adopt(state[q].data)
-                for op in self._fuse_pairs(chain):
-                    if op[0] == 'fused':
-                        _, lo, hi, G, noisy, tag = op
-                        G = self._dev(G)
-                        for q in (lo, hi):
-                            self._match_batch(state[q], G.shape[0])
-                        if state[lo].data.shape[0] != state[hi].data.shape[0]:
-                            B = max(state[lo].data.shape[0], state[hi].data.shape[0])
-                            self._match_batch(state[lo], B)
-                            self._match_batch(state[hi], B)
-                        self._merge_split(state, lo, hi, G, noisy, tag)
-                    else:
-                        i, g, oqs = op
-                        self._add_gate(state, i, _oqs=oqs, _gate=g)
+                    for qubits, _ in members:
+                        for q in qubits:
+                            adopt(state[q].data)
+                self._run_group(state, members)
             return task
 
-        parallel = getattr(_engine.get_prims(), 'name', '') == 'cuda' and len(strands) > 1
-        tasks = [make(chain) for chain in strands.values()]
+        tasks = [make(members) for members in groups.values()]
         run_strands(tasks, self.device, enabled=parallel)
-        if parallel and len(tasks) > 1:
-            for q in {q for _, _, oqs in ops for q in oqs}:
-                hand_over(state[q].data, self.device)
+        if parallel:
+            for qubits, _ in programs:
+                for q in qubits:
+                    hand_over(state[q].data, self.device)
+
+    _SWAP = tc.tensor([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]])
+
+    def _program(self, chain: list):
+        """Resolve one strand (gates in circuit order on a set of qubits that touch nothing else in this segment) into
+        primitive steps on host operands: ('1q', q, G [Bg,2,2,K], noisy) and ('2q', lo, lo+1, G [Bg,2,2,2,2,K], noisy,
+        tag). Returns (sorted qubits, steps)."""
+        steps = []
+        for op in self._fuse_pairs(chain):
+            if op[0] == 'fused':
+                _, lo, hi, G, noisy, tag = op
+                steps.append(('2q', lo, hi, G, noisy, tag))
+                continue
+            i, gate, oqs = op
+            if not gate or gate.name == 'MeasureZ':
+                continue
+            if not isinstance(gate, QuantumGate):
+                raise TypeError(f'Gate must be a QuantumGate, current type is {type(gate)}.')
+            if gate.single:
+                G, noisy = self._single_operand(gate)
+                steps.extend(('1q', q, G, noisy) for q in oqs)
+                continue
+            if len(oqs) != 2 or oqs[0] == oqs[1]:
+                raise ValueError('Invalid operating qubits for a two-qubit gate.')
+            lo, hi = min(oqs), max(oqs)
+            G, noisy = self._double_operand(gate, oqs)
+            swap = self._SWAP.to(self.dtype).reshape(1, 2, 2, 2, 2, 1)
+            for k in range(hi - 1, lo, -1):          # long-range gate: route through noiseless SWAPs (see
+                steps.append(('2q', k, k + 1, swap, False, None))      # _apply_two_qubits_gate)
+            steps.append(('2q', lo, lo + 1, G, noisy, i))
+            for k in range(lo + 1, hi):
+                steps.append(('2q', k, k + 1, swap, False, None))
+        qubits = sorted({q for st in steps for q in st[1:(2 if st[0] == '1q' else 3)]})
+        return qubits, steps
+
+    @staticmethod
+    def _signature(state, prog):
+        """Two strands with the same signature run the same kernels on tensors of the same shapes."""
+        qubits, steps = prog
+        rel = {q: j for j, q in enumerate(qubits)}
+        shapes = tuple(tuple(state[q].data.shape[1:]) for q in qubits)
+        flags = tuple((state[q].has_left, state[q].has_right, state[q].has_inner) for q in qubits)
+        seq = tuple((st[0],) + tuple(rel[q] for q in st[1:(2 if st[0] == '1q' else 3)]) + (tuple(st[-3 if st[0] == '2q' else -2].shape[1:]),)
+                    for st in steps)
+        return shapes, flags, seq
+
+    def _run_group(self, state: List[DenseNode], members: list):
+        """Execute strands with identical signatures as one batched launch sequence: member m's circuits occupy rows
+        m*B .. (m+1)*B of every stacked tensor. A single member runs in place (no stacking)."""
+        eng = self._engine()
+        M = len(members)
+        qubits0, steps0 = members[0]
+        if not steps0:
+            return
+        Bmax = max([state[q].data.shape[0] for qs, _ in members for q in qs] +
+                   [st[-3 if st[0] == '2q' else -2].shape[0] for _, sts in members for st in sts])
+        stacked = []
+        for j in range(len(qubits0)):
+            parts = []
+            for qs, _ in members:
+                node = state[qs[j]]
+                self._match_batch(node, Bmax)
+                parts.append(node.data)
+            stacked.append(parts[0] if M == 1 else tc.cat(parts, dim=0))
+        rel = {q: j for j, q in enumerate(qubits0)}
+        flags = [dict(l=state[q].has_left, r=state[q].has_right, i=state[q].has_inner) for q in qubits0]
+        ranks = {}
+        for t, st in enumerate(steps0):
+            Gs = [sts[t][-3 if st[0] == '2q' else -2] for _, sts in members]
+            if all(g.shape[0] == 1 for g in Gs) and all(g is Gs[0] or tc.equal(g, Gs[0]) for g in Gs[1:]):
+                G = Gs[0]
+            else:
+                G = tc.cat([g.expand(Bmax, *g.shape[1:]) for g in Gs], dim=0)
+            G = self._dev(G)
+            if st[0] == '1q':
+                j = rel[st[1]]
+                stacked[j] = eng.absorb_1q(stacked[j], G)
+                flags[j]['i'] = flags[j]['i'] or st[3]
+            else:
+                jl, jh = rel[st[1]], rel[st[2]]
+                stacked[jl], stacked[jh] = eng.split_2q(stacked[jl], stacked[jh], G, GLOBAL_MINIMUM)
+                flags[jl]['r'] = flags[jh]['l'] = True
+                flags[jh]['i'] = flags[jh]['i'] or st[4]
+                per_row = eng.stats.get('last_ranks')
+                for m, (_, sts) in enumerate(members):
+                    tag = sts[t][5]
+                    if tag is not None:
+                        ranks[tag] = (int(max(per_row[m * Bmax:(m + 1) * Bmax])) if per_row is not None
+                                      else int(stacked[jl].shape[4]))
+        if ranks:
+            self.last_stats.setdefault('split_ranks', {}).update(ranks)
+        for m, (qs, _) in enumerate(members):
+            for j, q in enumerate(qs):
+                node = state[q]
+                node.data = stacked[j] if M == 1 else stacked[j][m * Bmax:(m + 1) * Bmax]
+                node.has_left, node.has_right, node.has_inner = flags[j]['l'], flags[j]['r'], flags[j]['i']
 
     def forward(self, state: List[DenseNode]):
         self.evolve(state)

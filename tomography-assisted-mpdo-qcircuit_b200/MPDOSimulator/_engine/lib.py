@@ -51,9 +51,11 @@ SYMBOLS = {
                                  C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     'mpdo_qr_step': (C.c_int, [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                               C.c_void_p]),
-    'mpdo_bond_svd_step': (C.c_int, [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
-                                                    C.c_void_p, C.c_void_p, C.c_void_p]),
-    'mpdo_kappa_truncate': (C.c_int, [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mpdo_bond_svd_step': (C.c_int, [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double,
+                                                    C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p,
+                                                    C.c_void_p]),
+    'mpdo_kappa_truncate': (C.c_int, [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int), C.c_void_p,
+                                                     C.c_void_p, C.c_void_p]),
     'mpdo_split_2q': (C.c_int, [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
                                                C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     'mpdo_cast': (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),

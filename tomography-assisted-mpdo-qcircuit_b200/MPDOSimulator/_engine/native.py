@@ -53,8 +53,6 @@ class NativeEngine(Engine):
         return Q, Tn_new
 
     def bond_svd_step(self, Tl, Tr, chi, max_err=None):
-        if max_err is not None:
-            return super().bond_svd_step(Tl, Tr, chi, max_err)
         Tl, Tr = Tl.contiguous(), Tr.contiguous()
         Bn, lp, _, ap, l = Tl.shape
         _, _, _, a, r = Tr.shape
@@ -62,21 +60,29 @@ class NativeEngine(Engine):
         Tl_n = torch.empty((Bn, lp, 2, ap, k), dtype=Tl.dtype, device=Tl.device)
         Tr_n = torch.empty((Bn, k, 2, a, r), dtype=Tr.dtype, device=Tr.device)
         sv = torch.empty((Bn, l), dtype=torch.float64, device=Tr.device)
+        kk = C.c_int(k)
         self._call('mpdo_bond_svd_step', self.lib.mpdo_bond_svd_step, self.dt, self.npass, Bn, lp, ap, l, _p(Tl), a, r,
-                   _p(Tr), k, _p(Tl_n), _p(Tr_n), _p(sv), _stream())
+                   _p(Tr), k, -1.0 if max_err is None else float(max_err), C.byref(kk), _p(Tl_n), _p(Tr_n), _p(sv),
+                   _stream())
+        if kk.value != k:      # the relative-error rule kept fewer: the outputs were written densely with that rank
+            k = kk.value
+            Tl_n = Tl_n.view(-1)[:Bn * lp * 2 * ap * k].view(Bn, lp, 2, ap, k)
+            Tr_n = Tr_n.view(-1)[:Bn * k * 2 * a * r].view(Bn, k, 2, a, r)
         disc = sv[:, k:].clamp_min(0).sqrt() if self.npass == 1 else sv[:, k:]
         return Tl_n, Tr_n, disc
 
     def kappa_truncate(self, T, kappa, max_err=None):
-        if max_err is not None or kappa is None:
-            return super().kappa_truncate(T, kappa, max_err)
         T = T.contiguous()
         Bn, l, _, a, r = T.shape
-        k = min(int(kappa), a)
+        k = a if kappa is None else min(int(kappa), a)
         T_n = torch.empty((Bn, l, 2, k, r), dtype=T.dtype, device=T.device)
         disc = torch.empty((Bn,), dtype=torch.float64, device=T.device)
-        self._call('mpdo_kappa_truncate', self.lib.mpdo_kappa_truncate, self.dt, Bn, l, a, r, _p(T), k, _p(T_n),
-                   _p(disc), _stream())
+        kk = C.c_int(k)
+        self._call('mpdo_kappa_truncate', self.lib.mpdo_kappa_truncate, self.dt, Bn, l, a, r, _p(T), k,
+                   -1.0 if max_err is None else float(max_err), C.byref(kk), _p(T_n), _p(disc), _stream())
+        if kk.value != k:
+            k = kk.value
+            T_n = T_n.view(-1)[:Bn * l * 2 * k * r].view(Bn, l, 2, k, r)
         return T_n, disc.unsqueeze(1)
 
     def split_2q(self, Tlo, Thi, G, max_err=2.718281828459045e-8):

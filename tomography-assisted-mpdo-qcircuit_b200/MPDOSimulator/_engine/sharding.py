@@ -23,10 +23,11 @@ def gather_readout(local_rows, total, rank=None, world=None):
     w = local_rows.shape[1]
     padded = torch.zeros((per, w), dtype=local_rows.dtype, device=local_rows.device)
     padded[:local_rows.shape[0]] = local_rows
-    parts = [torch.empty_like(padded) for _ in range(world)]
-    dist.all_gather(parts, padded)
+    flat = torch.empty((world * per, w), dtype=local_rows.dtype, device=local_rows.device)
+    dist.all_gather_into_tensor(flat, padded)          # one collective: [world * per, w], rank-major
+    parts = flat.view(world, per, w)
     out = torch.empty((total, w), dtype=local_rows.dtype, device=local_rows.device)
     for r in range(world):
-        ids = list(range(total))[r::world]
-        out[ids] = parts[r][:len(ids)]
+        count = len(range(r, total, world))
+        out[r::world] = parts[r, :count]
     return out

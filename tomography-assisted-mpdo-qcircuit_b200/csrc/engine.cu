@@ -685,19 +685,24 @@ extern "C" int mpdo_qr_step(int dtype, int npass, int B, int l, int a, int r, co
   return contract(c.st, Rd, {1, 1, 1}, Tnx, {1, 1, 3}, To, {1, 1, 3});
 }
 
-// chi truncation step without the relative-error rule: k = min(chi, l). Tl [B,lp,2,ap,l], Tr [B,l,2,a,r].
+// chi truncation step: k = min(chi, l), further reduced by the relative-error rule when max_err >= 0 (SYNC: the kept
+// rank is read back; outputs are written densely with the kept rank into the caller's cap-sized buffers).
+// Tl [B,lp,2,ap,l], Tr [B,l,2,a,r].
 extern "C" int mpdo_bond_svd_step(int dtype, int npass, int B, int lp, int ap, int l, const void* Tl, int a, int r,
-                                  const void* Tr, int k, void* Tl_out, void* Tr_out, double* disc_out, void* stream) {
+                                  const void* Tr, int k, double max_err, int* k_out, void* Tl_out, void* Tr_out,
+                                  double* disc_out, void* stream) {
   Ctx c((cudaStream_t)stream, dtype, npass);
   c.set_batch(B);
   Tn TL = Tn::contig((void*)Tl, dtype, {B, lp, 2, ap, l});
   Tn TR = Tn::contig((void*)Tr, dtype, {B, l, 2, a, r});
-  Tn TLo = Tn::contig(Tl_out, dtype, {B, lp, 2, ap, k});
-  Tn TRo = Tn::contig(Tr_out, dtype, {B, k, 2, a, r});
   WideSvd w;
   EC(svd_wide(c, TR, {1, 1, 3}, &w));
   if (disc_out)  // singular values (squared in one-pass mode), all l of them, for the caller's truncation record
     MPDO_CUDA(cudaMemcpyAsync(disc_out, w.sv, sizeof(double) * (size_t)B * w.n, cudaMemcpyDeviceToDevice, c.st));
+  if (max_err >= 0) EC(keep_rank(c, w.sv, B, w.n, w.squared, k, max_err, true, &k));   // decompositions.py:117-134
+  if (k_out) *k_out = k;
+  Tn TLo = Tn::contig(Tl_out, dtype, {B, lp, 2, ap, k});
+  Tn TRo = Tn::contig(Tr_out, dtype, {B, k, 2, a, r});
   Tn right, left;
   EC(wide_right(c, w, k, dtype, &right));
   EC(contract(c.st, right, {1, 1, 1}, w.Mlast, {1, 1, 3}, TRo, {1, 1, 3}));
@@ -705,21 +710,20 @@ extern "C" int mpdo_bond_svd_step(int dtype, int npass, int B, int lp, int ap, i
   return contract(c.st, TL, {1, 3, 1}, transposed(left), {1, 1, 1}, TLo, {1, 3, 1}, false, true);
 }
 
-// kappa truncation without the relative-error rule: k = min(kappa, a). disc_out[b] = norm of the discarded part.
-extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const void* T, int k, void* T_out,
-                                   double* disc_out, void* stream) {
+// kappa truncation: k = min(kappa, a), further reduced by the relative-error rule when max_err >= 0 (SYNC; the output
+// is written densely with the kept rank). disc_out[b] = norm of the discarded part.
+extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const void* T, int k, double max_err,
+                                   int* k_out, void* T_out, double* disc_out, void* stream) {
   Ctx c((cudaStream_t)stream, dtype, 1);
   c.set_batch(B);
   Tn Tv = Tn::contig((void*)T, dtype, {B, l, 2, a, r});
-  Tn To = Tn::contig(T_out, dtype, {B, l, 2, k, r});
   Tn G;
   EC(gram_cols(c, Tv.permute({0, 1, 2, 4, 3}), {1, 3, 1}, &G));
   Tn Tperm = Tv.permute({0, 3, 1, 2, 4});   // [b | a | l,s,r]
-  Tn Operm = To.permute({0, 3, 1, 2, 4});   // [b | k | l,s,r]
   double* theta = nullptr;
   int thetaStride = a;
   bool done = false;
-  if (a >= 64 && a >= 8 * k) {
+  if (max_err < 0 && a >= 64 && a >= 8 * k) {
     Tn Vt;
     int conv = 0;
     EC(eigh_topk(c, G, k, &theta, &Vt, &conv));
@@ -728,6 +732,7 @@ extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const 
       Tn Vk = c.ar.alloc(dtype, {(long long)B, (long long)k, (long long)a});
       ARENA_OK(c);
       EC(copy_view(c.st, Vt.narrow(1, 0, k), Vk));
+      Tn Operm = Tn::contig(T_out, dtype, {B, l, 2, k, r}).permute({0, 3, 1, 2, 4});   // [b | k | l,s,r]
       EC(contract(c.st, Vk, {1, 1, 1}, Tperm, {1, 1, 3}, Operm, {1, 1, 3}));
       done = true;
     }
@@ -736,11 +741,19 @@ extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const 
     Tn Vh;
     EC(eigh(c, G, &theta, &Vh));
     thetaStride = a;
+    if (max_err >= 0) {   // the eigenvalues are the squared singular values of T over the inner index
+      double* sv = c.ar.reals((long long)B * a);
+      ARENA_OK(c);
+      MPDO_CUDA(cudaMemcpyAsync(sv, theta, sizeof(double) * (size_t)B * a, cudaMemcpyDeviceToDevice, c.st));
+      EC(keep_rank(c, sv, B, a, true, k, max_err, true, &k));
+    }
     Tn Vk = c.ar.alloc(dtype, {(long long)B, (long long)k, (long long)a});
     ARENA_OK(c);
     EC(copy_view(c.st, Vh.narrow(1, 0, k), Vk));
+    Tn Operm = Tn::contig(T_out, dtype, {B, l, 2, k, r}).permute({0, 3, 1, 2, 4});
     EC(contract(c.st, Vk, {1, 1, 1}, Tperm, {1, 1, 3}, Operm, {1, 1, 3}, true, false));
   }
+  if (k_out) *k_out = k;
   if (disc_out) {
     discarded_kernel<<<(B + 127) / 128, 128, 0, c.st>>>(B, a, k, (const double2*)G.p, theta, thetaStride, disc_out);
     EC(check_launch("discarded_kernel"));
