@@ -177,12 +177,13 @@ int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const void* T, in
  * [p_lo,p_hi,s_lo,s_hi,g] (Bg = 1 or B, same dtype as the state) -> T_lo' [B,l,2,a0,k], T_hi' [B,k,2,K*a1,r] with the
  * kept rank k from the reference rule ||s|| - ||s[:k]|| <= max_err. The rank is data dependent: `alloc(which, count,
  * user)` is called once it is known and returns device memory for `count` complex elements (which = 0: T_lo',
- * 1: T_hi'). SYNC (rank read-back).
+ * 1: T_hi'). SYNC (rank read-back). ranks_out (optional, HOST memory, B ints) receives the kept rank of every batch
+ * entry; *k_out is their maximum and entries with a smaller rank are padded with exact zeros.
  * Replaces: tn.contractors.optimal + tn.flatten_edges + tn.split_node at Circuit.py:104-124. */
 typedef void* (*mpdo_alloc_fn)(int which, int64_t count, void* user);
 int mpdo_split_2q(int dtype, int npass, int B, int l, int a0, int m, const void* Tlo, int a1, int r, const void* Thi,
                   int Bg, int K, const void* G, double max_err, mpdo_alloc_fn alloc, void* user, int* k_out,
-                  void* stream);
+                  int* ranks_out, void* stream);
 
 /* Elementwise dtype conversion between complex64 and complex128 (count complex elements). */
 int mpdo_cast(int dtypeIn, int dtypeOut, int64_t count, const void* in, void* out, void* stream);

@@ -323,15 +323,17 @@ class TensorCircuit(QuantumCircuit):
             if isinstance(g, QuantumGate) and not g.single and ((self.idealNoise and not g.ideal) or self.realNoise):
                 self.last_stats['noisy_2q_updates'] = self.last_stats.get('noisy_2q_updates', 0) + 1
 
-        # Strands whose step sequences and tensor shapes coincide (the bulk brick pairs of a layer) are stacked along
-        # the batch axis and run as ONE launch sequence (the kernels' batch dimension does not care whether its
-        # entries are circuits of a sweep or brick pairs of one circuit); the handful of distinct groups that remain
-        # (chain ends) are issued concurrently, one CUDA stream each.
+        # Strands are issued concurrently, one CUDA stream each. With MPDO_GROUPING=1 strands whose step sequences
+        # and tensor shapes coincide (the bulk brick pairs of a layer) are instead stacked along the batch axis and run
+        # as ONE launch sequence. Measured on B200 (profiles/r2_grouping.md): half the launches, but no faster on cfg2
+        # (148 vs 143 ms per layer) and slower on cfg4 (8.4 vs 12.9 circuits/s: one stream serialises the Gram
+        # contractions of one pair behind the factorisations of another, and a batch-wide stall of the top-kappa
+        # iteration sends every member down the full decomposition) - so it is opt-in.
         cuda = getattr(_engine.get_prims(), 'name', '') == 'cuda'
         programs = [self._program(chain) for chain in strands.values()]
         groups = {}
         for prog in programs:
-            key = self._signature(state, prog) if (cuda and os.environ.get('MPDO_GROUPING', '1') != '0') else id(prog)
+            key = self._signature(state, prog) if os.environ.get('MPDO_GROUPING', '0') == '1' else id(prog)
             groups.setdefault(key, []).append(prog)
         parallel = cuda and len(groups) > 1
 
@@ -433,7 +435,7 @@ class TensorCircuit(QuantumCircuit):
                 stacked[jl], stacked[jh] = eng.split_2q(stacked[jl], stacked[jh], G, GLOBAL_MINIMUM)
                 flags[jl]['r'] = flags[jh]['l'] = True
                 flags[jh]['i'] = flags[jh]['i'] or st[4]
-                per_row = eng.stats.get('last_ranks')
+                per_row = getattr(eng.tls, 'last_ranks', None)
                 for m, (_, sts) in enumerate(members):
                     tag = sts[t][5]
                     if tag is not None:

@@ -92,17 +92,38 @@ def svdKappa_left2right(_qubits: List[DenseNode], max_singular_values: Optional[
             raise ValueError(f'Axis name I_{q.index} not found')
         todo.append(q)
 
-    def make(q):
+    # Sites are independent. Sites whose tensors have the same shape (the bulk of a brickwork layer) are stacked along
+    # the batch axis and truncated by ONE launch sequence; the few distinct shapes that remain (chain ends) are issued
+    # concurrently, one CUDA stream each.
+    import os
+    import torch
+    cuda = getattr(_engine.get_prims(), 'name', '') == 'cuda'
+    groups = {}
+    for q in todo:
+        # (not with the relative-error rule: its kept rank is per site, and a stacked call pads to the group maximum)
+        key = (tuple(q.data.shape) if os.environ.get('MPDO_GROUPING', '0') == '1' and max_truncation_err is None
+               else id(q))
+        groups.setdefault(key, []).append(q)
+
+    def make(members):
         def task():
             if parallel:
-                adopt(q.data)
-            q.data, _ = eng.kappa_truncate(q.data, max_singular_values, max_truncation_err)
+                for q in members:
+                    adopt(q.data)
+            if len(members) == 1:
+                q = members[0]
+                q.data, _ = eng.kappa_truncate(q.data, max_singular_values, max_truncation_err)
+                return
+            B = members[0].data.shape[0]
+            out, _ = eng.kappa_truncate(torch.cat([q.data for q in members], dim=0), max_singular_values,
+                                        max_truncation_err)
+            for m, q in enumerate(members):
+                q.data = out[m * B:(m + 1) * B]
         return task
 
-    # sites are independent: issue them concurrently (one CUDA stream each)
     device = _qubits[0].data.device
-    parallel = getattr(_engine.get_prims(), 'name', '') == 'cuda' and len(todo) > 1
-    run_strands([make(q) for q in todo], device, enabled=parallel)
-    if parallel and len(todo) > 1:
+    parallel = cuda and len(groups) > 1
+    run_strands([make(members) for members in groups.values()], device, enabled=parallel)
+    if parallel:
         for q in todo:
             hand_over(q.data, device)

@@ -57,7 +57,8 @@ SYMBOLS = {
     'mpdo_kappa_truncate': (C.c_int, [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int), C.c_void_p,
                                                      C.c_void_p, C.c_void_p]),
     'mpdo_split_2q': (C.c_int, [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
-                                               C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
+                                               C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                               C.c_void_p]),
     'mpdo_cast': (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     'mpdo_trim_pools': (C.c_int, []),
     'mpdo_pool_stats': (C.c_int, [C.POINTER(C.c_int64)] * 2),

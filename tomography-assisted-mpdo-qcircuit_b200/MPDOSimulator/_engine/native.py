@@ -100,9 +100,11 @@ class NativeEngine(Engine):
 
         cb = ALLOC_FN(alloc)
         k = C.c_int(0)
+        rows = (C.c_int * Bn)()
         self._call('mpdo_split_2q', self.lib.mpdo_split_2q, self.dt, self.npass, Bn, l, a0, m, _p(Tlo), a1, r, _p(Thi),
                    Bg, K, _p(G), -1.0 if max_err is None else float(max_err), C.cast(cb, C.c_void_p), None,
-                   C.byref(k), _stream())
+                   C.byref(k), rows, _stream())
         kk = k.value
         self.stats['last_rank'] = kk
+        self.tls.last_ranks = list(rows)          # kept rank of every batch entry (kk is their maximum)
         return outs[0].view(Bn, l, 2, a0, kk), outs[1].view(Bn, kk, 2, K * a1, r)

@@ -19,6 +19,7 @@ quantities. The inner index order is (new Kraus index major, old index minor) - 
 an index that is only ever traced against its own conjugate.
 """
 import os
+import threading
 
 import torch
 
@@ -36,6 +37,7 @@ class Engine:
         self.jacobi_tol = 1e-10 if self.f32 else 1e-15   # fp32-stored states: see csrc/engine.cu Ctx
         self.stats = {'discarded': []}
         self._omega = {}         # fixed start blocks of the subspace iteration, per (n, block, device)
+        self.tls = threading.local()   # per-thread results of the last call (strands run on several host threads)
 
     # ------------------------------------------------------------------------------------------
     # helpers
@@ -240,6 +242,7 @@ class Engine:
             p.contract(XU, (1, 1, 1), Alast.permute(0, 2, 1), (1, 1, 1), UL, (1, 1, 1), conjB=True)
             Zc = p.rowscale(Wh_, s, k, 0.5, 0.0, 0, C128 if F_hi is not None else self.dtype).reshape(Bn, k, 2, K, y)
         self.stats['last_rank'] = k
+        self.tls.last_ranks = None       # per-entry ranks are only reported by the native engine
 
         # Tlo'[b,l,p0,a0,j] = sum_x Q'[(l,a0),x] conj(UL[j,(x,p0)])
         Tlo_n = self._empty((Bn, l, 2, a0, k), Tlo)

@@ -359,10 +359,13 @@ static int rowscale(Ctx& c, const Tn& V, const double* lam, int lamStride, int r
 }
 
 // kept rank (batch maximum) by the reference rule; zero-tails sv in place. SYNC when max_err >= 0.
-static int keep_rank(Ctx& c, double* sv, int B, int n, bool squared, int cap, double max_err, bool relative, int* k) {
+static int keep_rank(Ctx& c, double* sv, int B, int n, bool squared, int cap, double max_err, bool relative, int* k,
+                     int* rows_out = nullptr) {
   if (cap < 0 || cap > n) cap = n;
   if (max_err < 0) {
     *k = cap;
+    if (rows_out)
+      for (int i = 0; i < B; ++i) rows_out[i] = cap;
     return 0;
   }
   int32_t* dk = (int32_t*)c.ar.raw(sizeof(int32_t) * (size_t)B);
@@ -379,6 +382,8 @@ static int keep_rank(Ctx& c, double* sv, int B, int n, bool squared, int cap, do
   MPDO_CUDA(cudaStreamSynchronize(c.st));
   int best = 1;
   for (int i = 0; i < B; ++i) best = std::max(best, (int)hk[i]);
+  if (rows_out)
+    for (int i = 0; i < B; ++i) rows_out[i] = (int)hk[i];
   *k = best;
   return 0;
 }
@@ -764,9 +769,10 @@ extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const 
 // Two-qubit gate absorption + split (Circuit.py:74-136). G [Bg,2,2,2,2,K] in (lo, hi) order, same dtype as the state.
 // The kept rank is data dependent: alloc(which, count, user) is called once the rank is known and must return device
 // memory for count complex elements (which = 0: T_lo' [B,l,2,a0,k]; 1: T_hi' [B,k,2,K*a1,r]). SYNC (rank read-back).
+// ranks_out (optional, host memory, B ints): the kept rank of every batch entry (k_out is their maximum).
 extern "C" int mpdo_split_2q(int dtype, int npass, int B, int l, int a0, int m, const void* Tlo, int a1, int r,
                              const void* Thi, int Bg, int K, const void* G, double max_err, mpdo_alloc_fn alloc,
-                             void* user, int* k_out, void* stream) {
+                             void* user, int* k_out, int* ranks_out, void* stream) {
   Ctx c((cudaStream_t)stream, dtype, npass);
   c.set_batch(B);
   const long long Bn = B;
@@ -833,7 +839,7 @@ extern "C" int mpdo_split_2q(int dtype, int npass, int B, int l, int a0, int m, 
   if (nrow <= ncol) {
     WideSvd w;
     EC(svd_wide(c, Cv, {1, 1, 1}, &w));
-    EC(keep_rank(c, w.sv, B, w.n, w.squared, -1, max_err, false, &k));
+    EC(keep_rank(c, w.sv, B, w.n, w.squared, -1, max_err, false, &k, ranks_out));
     EC(wide_left(c, w, k, MPDO_C128, &UL));
     Tn right;
     EC(wide_right(c, w, k, MPDO_C128, &right));
@@ -846,7 +852,7 @@ extern "C" int mpdo_split_2q(int dtype, int npass, int B, int l, int a0, int m, 
     double* s;
     EC(orth_cols(c, Cv, {1, 1, 1}, &Alast, &Xs, &R));
     EC(decompose(c, R, true, &s, &Wh_, &Uh_));  // R = Uh_^h diag(s) Wh_
-    EC(keep_rank(c, s, B, (int)ncol, false, -1, max_err, false, &k));
+    EC(keep_rank(c, s, B, (int)ncol, false, -1, max_err, false, &k, ranks_out));
     EC(rowscale(c, Uh_, s, (int)ncol, k, 0.5, 0.0, 0, MPDO_C128, &su));
     XU = c.ar.alloc(MPDO_C128, {Bn, (long long)k, ncol});
     UL = c.ar.alloc(MPDO_C128, {Bn, (long long)k, nrow});
