@@ -198,6 +198,15 @@ int mpdo_timing_enable(int on);
 int mpdo_timing_summary(int cls, double minFlops, double* seconds, double* flops, double* bytes, int64_t* launches,
                         double* maxFlopsSeconds, double* maxFlops);
 
+/* Tensor-core path of mpdo_contract for complex64 applies (tcgen05.mma kind::tf32 with a 3xTF32 split, TMA operand
+ * tiles, accumulators in TMEM; csrc/tc_apply.cu). Eligible: all-complex64, fp32 accumulation, beta = 0, A and C plain
+ * row-major matrices per batch entry (k / j contiguous), M >= 512, K >= 16 and even, N >= 8 and even; op(B) may be any
+ * composite-index view. mode 0 routes those products to the FFMA tiles again (A/B measurements, parity tests);
+ * mode 1 (default) picks the column tile so that the fp32 accumulator chains in TMEM stay short (tcgen05 accumulates
+ * with truncation: relative error <= 7e-7 measured up to K = 512, like the FFMA tiles); mode 2 always uses the widest
+ * tile (about 1.35x faster at K >= 256, relative error 1.3e-6 .. 1.8e-6). Returns the previous mode. */
+int mpdo_tc_enable(int mode);
+
 /* Hands the scratch memory cached by the step-level entry points (one stream-ordered pool per calling thread) back
  * to the driver. The step functions return cudaErrorMemoryAllocation (2) only after trying this themselves; a caller
  * that shares the device with another caching allocator (torch) releases that cache and retries. */

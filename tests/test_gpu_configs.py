@@ -110,7 +110,9 @@ def test_batched_sweep_is_deterministic_and_matches_singles(cuda_prims):
         return torch.stack([dmOperations.pauli_expect(dmn, 2, q).reshape(-1) for q in range(n)], 1).cpu()
 
     a, b = run(ids), run(ids)
-    assert torch.equal(a, b) or (a - b).abs().max().item() < 1e-13
+    # (the kappa step remembers per shape whether its subspace iteration stalled and may take the full decomposition
+    # instead on a later call: both are exact solvers, so repeat runs agree to solver tolerance, not bit for bit)
+    assert torch.equal(a, b) or (a - b).abs().max().item() < 1e-11
     for i in ids:
         single = run([i])
         assert (a[i] - single[0]).abs().max().item() < 1e-10

@@ -22,7 +22,7 @@ from .AbstractCircuit import QuantumCircuit
 from .NoiseChannel import NoiseChannel
 from .QuantumGates.AbstractGate import QuantumGate
 from .QuantumGates.SingleGates import MeasureX, MeasureY
-from .TNNOptimizer import bondTruncate, svdKappa_left2right, checkConnectivity
+from .TNNOptimizer import bondTruncate, svdKappa_left2right, checkConnectivity, truncateLayer  # noqa: F401
 from .Tools import count_item
 from .dmOperations import DmNodes
 
@@ -278,10 +278,8 @@ class TensorCircuit(QuantumCircuit):
             if 'truncate' in name:
                 self._run_segment(state, segment)
                 if checkConnectivity(state):
-                    bondTruncate(state, max_singular_values=self.chi, max_truncation_err=self.max_truncation_err)
-                    if not self.ideal:
-                        svdKappa_left2right(state, max_singular_values=self.kappa,
-                                            max_truncation_err=self.max_truncation_err)
+                    truncateLayer(state, chi=self.chi, kappa=self.kappa, max_truncation_err=self.max_truncation_err,
+                                  noisy=not self.ideal)
             elif 'barrier' in name:
                 pass
             else:

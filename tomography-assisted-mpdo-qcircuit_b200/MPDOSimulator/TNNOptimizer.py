@@ -8,7 +8,7 @@ from ._engine.strands import adopt, hand_over, run_strands
 from ._node import DenseNode
 
 __all__ = ['qr_left2right', 'svd_left2right', 'svd_right2left', 'svdKappa_left2right', 'bondTruncate',
-           'checkConnectivity']
+           'checkConnectivity', 'truncateLayer']
 
 
 def checkConnectivity(_qubits: List[DenseNode]):
@@ -127,3 +127,70 @@ def svdKappa_left2right(_qubits: List[DenseNode], max_singular_values: Optional[
     if parallel:
         for q in todo:
             hand_over(q.data, device)
+
+
+def _needs_kappa(q: DenseNode, kappa: Optional[int]):
+    return not (kappa is not None and (not q.has_inner or q.data.shape[3] <= kappa))
+
+
+def truncateLayer(_qubits: List[DenseNode], chi: Optional[int] = None, kappa: Optional[int] = None,
+                  max_truncation_err: Optional[float] = None, noisy: bool = True):
+    """What a `truncate` layer does (Circuit.py:476-481): bondTruncate, then - for a noisy circuit -
+    svdKappa_left2right. Same results as calling the two in turn; on a CUDA device the inner-index truncation of site
+    i is issued on a side stream as soon as the right-to-left sweep has passed bond (i-1, i) - the site is final from
+    then on - so the independent kappa steps can run beside the sequential sweep instead of after it. Opt-in
+    (MPDO_KAPPA_PIPELINE=1): measured on B200 (profiles/r2_grouping.md) it does not shorten the cfg2 layer - the sweep's
+    factorisations and the kappa Gram contractions compete for the same SMs - and it makes step times less regular."""
+    import os
+    import torch
+    from ._engine.strands import _pool, _streams
+    do_bond = not (chi is None and max_truncation_err is None)
+    do_kappa = noisy and not (kappa is None and max_truncation_err is None)
+    cuda = getattr(_engine.get_prims(), 'name', '') == 'cuda'
+    if not (do_bond and do_kappa and cuda and len(_qubits) > 2) or os.environ.get('MPDO_KAPPA_PIPELINE', '0') != '1':
+        if do_bond:
+            bondTruncate(_qubits, max_singular_values=chi, max_truncation_err=max_truncation_err)
+        if do_kappa:
+            svdKappa_left2right(_qubits, max_singular_values=kappa, max_truncation_err=max_truncation_err)
+        return
+    qr_left2right(_qubits)
+    eng = _engine_of(_qubits)
+    dev = _qubits[0].data.device
+    main = torch.cuda.current_stream(dev)
+    from ._engine.strands import MAX_WORKERS
+    streams = _streams(dev, min(MAX_WORKERS, len(_qubits)))
+    futures, used = [], []
+
+    def kappa_task(q, stream, event):
+        with torch.cuda.device(dev), torch.cuda.stream(stream):
+            stream.wait_event(event)
+            adopt(q.data)
+            if not q.has_inner:
+                raise ValueError(f'Axis name I_{q.index} not found')
+            q.data, _ = eng.kappa_truncate(q.data, kappa, max_truncation_err)
+
+    def launch(q):
+        if not _needs_kappa(q, kappa):
+            return
+        ev = torch.cuda.Event()
+        ev.record(main)
+        stream = streams[len(futures) % len(streams)]
+        used.append((q, stream))
+        futures.append(_pool().submit(kappa_task, q, stream, ev))
+
+    for idx in range(len(_qubits) - 1, 0, -1):
+        left, right = _qubits[idx - 1], _qubits[idx]
+        left.data, right.data, _ = eng.bond_svd_step(left.data, right.data, chi, max_truncation_err)
+        launch(right)
+    launch(_qubits[0])
+    errors = []
+    for f in futures:
+        try:
+            f.result()
+        except BaseException as exc:   # re-raised below, after every stream has been joined
+            errors.append(exc)
+    for q, stream in used:
+        main.wait_stream(stream)
+        hand_over(q.data, dev)
+    if errors:
+        raise errors[0]

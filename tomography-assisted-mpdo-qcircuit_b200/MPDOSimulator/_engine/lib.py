@@ -60,6 +60,7 @@ SYMBOLS = {
                                                C.c_double, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                                C.c_void_p]),
     'mpdo_cast': (C.c_int, [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'mpdo_tc_enable': (C.c_int, [C.c_int]),
     'mpdo_trim_pools': (C.c_int, []),
     'mpdo_pool_stats': (C.c_int, [C.POINTER(C.c_int64)] * 2),
     'mpdo_timing_enable': (C.c_int, [C.c_int]),

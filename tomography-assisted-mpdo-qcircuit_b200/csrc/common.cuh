@@ -95,6 +95,11 @@ __device__ __forceinline__ void matrix_barrier(unsigned* bar, unsigned nblk, uns
 }
 #endif
 
+// tc_apply.cu: tcgen05 / TMA path of the complex64 apply contractions. 1 = issued, 0 = not eligible, else error.
+namespace tc {
+int try_apply(const mpdo_contract_desc& d, const void* A, const void* B, void* C, cudaStream_t st);
+}
+
 // jacobi.cu: mpdo_jacobi_rows with an optional per-matrix count of non-zero leading rows (device memory)
 int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchStride, void* Y, double tol,
                        int maxSweeps, int32_t* work, const int* rank, int rankStride, void* stream);

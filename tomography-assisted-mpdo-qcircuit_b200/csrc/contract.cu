@@ -354,7 +354,14 @@ extern "C" int mpdo_contract(const mpdo_contract_desc* dp, const void* A, const 
   cudaStream_t st = (cudaStream_t)stream;
   const int key = (d.dtypeA << 2) | (d.dtypeB << 1) | d.dtypeC;
   const bool f64 = d.acc64 || key != 0;
-  if (!f64) return launch_contract<float2, float2, float2, float>(d, A, B, C, st);
+  if (!f64) {
+    // tall complex64 applies with a small second operand go to the tcgen05 / TMA tile (tc_apply.cu); everything
+    // else (composite-index views, short products) stays on the FFMA tiles
+    const int rc = tc::try_apply(d, A, B, C, st);
+    if (rc == 1) return 0;
+    if (rc != 0) return rc;
+    return launch_contract<float2, float2, float2, float>(d, A, B, C, st);
+  }
   // Measured on B200 (tools/bench_contract.py, profiles/r1_contract_ncu.md): DMMA tiles 18.1 TFLOP/s on the kappa
   // Gram matrix (1024 x 1024 x 8192, complex64 in, fp64 accumulate) and 26.5 TFLOP/s on a complex128-operand apply
   // (512 x 8192 x 512), scalar DFMA tiles 16.5 and 22.0. B200 retires DMMA at about the DFMA rate, so the tensor form
