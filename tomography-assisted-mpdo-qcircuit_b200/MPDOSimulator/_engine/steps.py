@@ -198,6 +198,8 @@ class Engine:
             Alo, Xs_lo = None, None
             Rp = Xlo.reshape(Bn, x, 2 * m).to(C128)
         # right factor: rows (m,s1), cols (a1,r)
+        if self.npass == 1 and a1 * r > 2 * m and not os.environ.get('MPDO_SPLIT_VIA_CORE'):
+            return self._split_2q_coreless(Tlo, Thi, G, max_err, Alo, Xs_lo, Rp, x)
         if a1 * r > 2 * m:
             Mhi, F_hi, Lh_hi = self.orth_rows(Thi, (1, 2, 2))   # Qt' = F_hi . Mhi ; Thi = Lh_hi^h . Qt'
             y = 2 * m
@@ -267,6 +269,63 @@ class Engine:
             Thi_n = Zc.reshape(Bn, k, 2, K * a1, r)
             if Thi_n.dtype != self.dtype:
                 Thi_n = Thi_n.to(self.dtype)
+        return Tlo_n, Thi_n
+
+    def _split_2q_coreless(self, Tlo, Thi, G, max_err, Alo, Xs_lo, Rp, x):
+        """complex64 states, wide right factor (csrc/engine.cu mpdo_split_2q, same sequence): the (2x) x (2Ky) core is
+        never formed. With Lam = T_hi T_hi^h over (a1,r) and Gam[p0 s0 s1; p0' s0' s1'] = sum_{p1,g} G conj(G),
+          C C^h[(x,p0),(x',p0')] = sum R'[x,s0,m] conj(R'[x',s0',m']) Lam[(m,s1),(m',s1')] Gam[p0 s0 s1; p0' s0' s1'],
+        and sqrt(S) Vh is rebuilt from the site itself:
+          T_hi'[j,p1,(g,a1),r] = sum_{m,s1} Y[j,p1,g,m,s1] T_hi[m,s1,a1,r],
+          Y = sum_{x,p0,s0} W[j,x,p0] R'[x,s0,m] G[p0,p1,s0,s1,g],  W = S^-1/4 U^h."""
+        p = self.p
+        Bn, l, _, a0, m = Tlo.shape
+        _, _, _, a1, r = Thi.shape
+        Bg, K = G.shape[0], G.shape[-1]
+        dev = Tlo.device
+        Lam = self._gram_rows(Thi, (1, 2, 2))                                   # [B, (m,s1), (m',s1')]
+        T1 = torch.empty((Bn, 2, x * 2, 2 * m), dtype=C128, device=dev)         # [b, s1, (x,s0), (m',s1')]
+        p.contract(Rp.reshape(Bn, 1, x * 2, m).expand(Bn, 2, x * 2, m), (2, 1, 1),
+                   Lam.reshape(Bn, m, 2, 2 * m).permute(0, 2, 1, 3), (2, 1, 1), T1, (2, 1, 1))
+        T2s = torch.empty((Bn, x, x, 2, 2, 2, 2), dtype=C128, device=dev)       # [b, x, x', s0, s1, s0', s1']
+        p.contract(T1.reshape(Bn, 2, x, 2, m, 2).permute(0, 5, 1, 2, 3, 4), (2, 3, 1),
+                   Rp.reshape(Bn, 1, x, 2, m).expand(Bn, 2, x, 2, m).permute(0, 1, 4, 2, 3), (2, 1, 2),
+                   T2s.permute(0, 6, 4, 1, 3, 2, 5), (2, 3, 2), conjB=True)
+        Gc = G.to(C128).contiguous()                                            # [bg, p0, p1, s0, s1, g]
+        Gam = torch.empty((Bg, 8, 8), dtype=C128, device=dev)
+        p.contract(Gc.permute(0, 1, 3, 4, 2, 5), (1, 3, 2), Gc.permute(0, 2, 5, 1, 3, 4), (1, 2, 3), Gam, (1, 1, 1),
+                   conjB=True)
+        GG = torch.empty((Bn, x, 2, x, 2), dtype=C128, device=dev)              # [b, (x,p0), (x',p0')]
+        GamV = Gam.reshape(Bg, 2, 2, 2, 2, 2, 2).permute(0, 1, 4, 2, 3, 5, 6)
+        if Bg == 1:
+            GamV = GamV.expand(Bn, 2, 2, 2, 2, 2, 2)
+        p.contract(GamV, (1, 2, 4), T2s.reshape(Bn, x * x, 16).permute(0, 2, 1), (1, 1, 1),
+                   GG.permute(0, 2, 4, 1, 3), (1, 2, 2))
+        GGm = GG.reshape(Bn, 2 * x, 2 * x)
+        lam, Uh = p.eigh_psd(GGm, self.jacobi_tol, rank_revealing=self._rr(GGm))
+        k = self._keep(lam, None, max_err, False, squared=True)
+        self.stats['last_rank'] = k
+        self.tls.last_ranks = None
+        UL = p.rowscale(Uh, lam, k, 0.25, self.null_tol, 0, C128)               # sqrt(s_j) conj(U[(x,p0), j])
+        Wr = p.rowscale(Uh, lam, k, -0.25, self.null_tol, 0, C128)
+        V = torch.empty((Bn, k, 2, 2, m), dtype=C128, device=dev)               # [b, j, p0, s0, m]
+        p.contract(Wr.reshape(Bn, k, x, 2).permute(0, 3, 1, 2), (2, 1, 1),
+                   Rp.reshape(Bn, 1, x, 2 * m).expand(Bn, 2, x, 2 * m), (2, 1, 1), V.permute(0, 2, 1, 3, 4), (2, 1, 2))
+        Gq = Gc.permute(0, 2, 5, 4, 1, 3).contiguous()                          # [bg, p1, g, s1, p0, s0]
+        Y = torch.empty((Bn, k, 2, K, m, 2), dtype=self.dtype, device=dev)      # [b, j, p1, g, m, s1]
+        GqV = Gq.reshape(Bg, 1, 4 * K, 4).expand(Bn, k, 4 * K, 4)
+        p.contract(GqV, (2, 1, 1), V.reshape(Bn, k, 4, m), (2, 1, 1), Y.permute(0, 1, 2, 3, 5, 4), (2, 3, 1))
+        Tlo_n = self._empty((Bn, l, 2, a0, k), Tlo)
+        ULv = UL.reshape(Bn, k, x, 2)
+        if Alo is not None:
+            W = torch.empty((Bn, 2 * m, 2, k), dtype=self.dtype, device=dev)
+            p.contract(Xs_lo.permute(0, 2, 1), (1, 1, 1), ULv.permute(0, 2, 3, 1), (1, 1, 2), W.reshape(Bn, 2 * m, 2 * k),
+                       (1, 1, 1), conjA=True, conjB=True)
+            p.contract(Alo, (1, 2, 2), W.reshape(Bn, 2, m, 2, k), (1, 2, 2), Tlo_n.permute(0, 1, 3, 2, 4), (1, 2, 2))
+        else:
+            Tlo_n.copy_(ULv.reshape(Bn, k, l, a0, 2).permute(0, 2, 4, 3, 1).conj())
+        Thi_n = self._empty((Bn, k, 2, K * a1, r), Thi)
+        p.contract(Y.reshape(Bn, k * 2 * K, m, 2), (1, 1, 2), Thi, (1, 2, 2), Thi_n.reshape(Bn, k * 2 * K, a1, r), (1, 1, 2))
         return Tlo_n, Thi_n
 
     # ------------------------------------------------------------------------------------------

@@ -812,6 +812,88 @@ extern "C" int mpdo_split_2q(int dtype, int npass, int B, int l, int a0, int m, 
   Tn Mhi, F_hi, Lh_hi;
   bool orthHi = (long long)a1 * r > 2LL * m;
   long long y;
+  static const bool oldSplit = getenv("MPDO_SPLIT_VIA_CORE") != nullptr;   // A/B knob: always form the core
+  if (c.npass == 1 && orthHi && !oldSplit) {
+    // ---- complex64 states, wide right factor: the core is never formed ------------------------------------------
+    // Theta = (Q' x 1) . C . (1 x Qt') and the split only needs (i) the Gram matrix of the core over its columns and
+    // (ii) sqrt(S) Vh = S^-1/2 U^h Theta. With Lam = T_hi T_hi^h over (a1, r) [the 2m x 2m Gram matrix of the right
+    // site] and Gam[p0 s0 s1 ; p0' s0' s1'] = sum_{p1,g} G conj(G) [8 x 8, gate only]:
+    //   C C^h [(x,p0),(x',p0')] = sum R'[x,s0,m] conj(R'[x',s0',m']) Lam[(m,s1),(m',s1')] Gam[p0 s0 s1 ; p0' s0' s1']
+    // which is ~0.2 GFLOP of small contractions instead of the 2x x 2Ky core (268 MB for a fused rzz at chi = 64),
+    // its 17 GFLOP fp64 Gram matrix and the 25 + 13 GFLOP of Zc = right . C and Zc . F_hi; no factorisation of the
+    // right site is needed at all. The kept right factor is rebuilt from the site itself:
+    //   T_hi'[j,p1,(g,a1),r] = sum_{m,s1} Y[j,p1,g,m,s1] T_hi[m,s1,a1,r],  Y = sum_{x,p0,s0} W[j,x,p0] R'[x,s0,m] G[p0,p1,s0,s1,g]
+    // with W = S^-1/4 U^h. Same sqrt(S) | sqrt(S) split, same rank rule on the same singular values.
+    Tn Lam;
+    EC(gram_rows(c, THI, {1, 2, 2}, &Lam));                                  // [B, (m,s1), (m',s1')]
+    const long long mm = m;
+    Tn T1 = c.ar.alloc(MPDO_C128, {Bn, 2, x * 2, 2 * mm});                   // [b, s1, (x,s0), (m',s1')]
+    ARENA_OK(c);
+    EC(contract(c.st, Rp.view({Bn, 1, x * 2, mm}).expand(1, 2), {2, 1, 1},
+                Lam.view({Bn, mm, 2, 2 * mm}).permute({0, 2, 1, 3}), {2, 1, 1}, T1, {2, 1, 1}));
+    Tn T2s = c.ar.alloc(MPDO_C128, {Bn, x, x, 2, 2, 2, 2});                  // [b, x, x', s0, s1, s0', s1']
+    ARENA_OK(c);
+    EC(contract(c.st, T1.view({Bn, 2, x, 2, mm, 2}).permute({0, 5, 1, 2, 3, 4}), {2, 3, 1},
+                Rp.view({Bn, 1, x, 2, mm}).expand(1, 2).permute({0, 1, 4, 2, 3}), {2, 1, 2},
+                T2s.permute({0, 6, 4, 1, 3, 2, 5}), {2, 3, 2}, false, true));
+    Tn Gc = c.ar.alloc(MPDO_C128, {(long long)Bg, 2, 2, 2, 2, (long long)K});
+    Tn Gam = c.ar.alloc(MPDO_C128, {(long long)Bg, 8, 8});                   // [bg, (p0,s0,s1), (p0',s0',s1')]
+    ARENA_OK(c);
+    EC(copy_view(c.st, Gv, Gc));
+    EC(contract(c.st, Gc.permute({0, 1, 3, 4, 2, 5}), {1, 3, 2}, Gc.permute({0, 2, 5, 1, 3, 4}), {1, 2, 3}, Gam, {1, 1, 1},
+                false, true));
+    Tn GG = c.ar.alloc(MPDO_C128, {Bn, x, 2, x, 2});                         // [b, (x,p0), (x',p0')]
+    ARENA_OK(c);
+    {
+      Tn GamV = Gam.view({(long long)Bg, 2, 2, 2, 2, 2, 2}).permute({0, 1, 4, 2, 3, 5, 6});   // [bg | p0,p0' | s0,s1,s0',s1']
+      if (Bg == 1) GamV = GamV.expand(0, Bn);
+      EC(contract(c.st, GamV, {1, 2, 4}, T2s.view({Bn, x * x, 16}).permute({0, 2, 1}), {1, 1, 1},
+                  GG.permute({0, 2, 4, 1, 3}), {1, 2, 2}));
+    }
+    double* lam;
+    Tn Uh;
+    EC(eigh(c, GG.view({Bn, 2 * x, 2 * x}), &lam, &Uh));
+    int k = 0;
+    EC(keep_rank(c, lam, B, (int)(2 * x), true, -1, max_err, false, &k, ranks_out));
+    Tn UL, Wr;
+    EC(rowscale(c, Uh, lam, (int)(2 * x), k, 0.25, c.null_tol, 0, MPDO_C128, &UL));     // sqrt(s_j) conj(U[(x,p0), j])
+    EC(rowscale(c, Uh, lam, (int)(2 * x), k, -0.25, c.null_tol, 0, MPDO_C128, &Wr));
+    Tn V = c.ar.alloc(MPDO_C128, {Bn, (long long)k, 2, 2, mm});               // [b, j, p0, s0, m]
+    Tn Gq = c.ar.alloc(MPDO_C128, {(long long)Bg, 2, (long long)K, 2, 2, 2});  // [bg, p1, g, s1, p0, s0]
+    Tn Y = c.ar.alloc(dtype, {Bn, (long long)k, 2, (long long)K, mm, 2});      // [b, j, p1, g, m, s1]
+    ARENA_OK(c);
+    EC(contract(c.st, Wr.view({Bn, (long long)k, x, 2}).permute({0, 3, 1, 2}), {2, 1, 1},
+                Rp.view({Bn, 1, x, 2 * mm}).expand(1, 2), {2, 1, 1}, V.permute({0, 2, 1, 3, 4}), {2, 1, 2}));
+    EC(copy_view(c.st, Gv.permute({0, 2, 5, 4, 1, 3}), Gq));
+    {
+      Tn GqV = Gq.view({(long long)Bg, 1, 4LL * K, 4});
+      if (Bg == 1) GqV = GqV.expand(0, Bn);
+      GqV = GqV.expand(1, k);
+      EC(contract(c.st, GqV, {2, 1, 1}, V.view({Bn, (long long)k, 4, mm}), {2, 1, 1}, Y.permute({0, 1, 2, 3, 5, 4}),
+                  {2, 3, 1}));
+    }
+    *k_out = k;
+    void* plo = alloc(0, (int64_t)Bn * l * 2 * a0 * k, user);
+    void* phi = alloc(1, (int64_t)Bn * k * 2 * K * a1 * r, user);
+    if (!plo || !phi) return fail(MPDO_EINVAL, "mpdo_split_2q: output allocation failed");
+    Tn Tlo_n = Tn::contig(plo, dtype, {Bn, l, 2, a0, (long long)k});
+    Tn Thi_n = Tn::contig(phi, dtype, {Bn, (long long)k, 2, (long long)K * a1, r});
+    Tn ULv = UL.view({Bn, (long long)k, x, 2});
+    if (orthLo) {
+      Tn W = c.ar.alloc(dtype, {Bn, 2LL * m, 2, (long long)k});
+      ARENA_OK(c);
+      EC(contract(c.st, transposed(Xs_lo), {1, 1, 1}, ULv.permute({0, 2, 3, 1}), {1, 1, 2}, W.view({Bn, 2LL * m, 2LL * k}),
+                  {1, 1, 1}, true, true));
+      EC(contract(c.st, Alo, {1, 2, 2}, W.view({Bn, 2, (long long)m, 2, (long long)k}), {1, 2, 2},
+                  Tlo_n.permute({0, 1, 3, 2, 4}), {1, 2, 2}));
+    } else {
+      Tn src = UL.view({Bn, (long long)k, (long long)l, (long long)a0, 2}).permute({0, 2, 4, 3, 1});
+      EC(copy_view(c.st, src, Tlo_n, true));
+    }
+    // the one big product of the split: [(j,p1,g) x (m,s1)] . [(m,s1) x (a1,r)], complex64 (tensor-core tile)
+    return contract(c.st, Y.view({Bn, (long long)k * 2 * K, mm, 2}), {1, 1, 2}, THI, {1, 2, 2},
+                    Thi_n.view({Bn, (long long)k * 2 * K, (long long)a1, (long long)r}), {1, 1, 2});
+  }
   if (orthHi) {
     EC(orth_rows(c, THI, {1, 2, 2}, &Mhi, &F_hi, &Lh_hi));
     y = 2LL * m;

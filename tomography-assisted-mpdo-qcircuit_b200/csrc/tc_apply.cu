@@ -30,7 +30,11 @@
 // Every mbarrier wait is bounded: a protocol error traps instead of hanging the device.
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <atomic>
+#include <mutex>
+#include <unordered_map>
 
 #include "engine.cuh"
 
@@ -42,7 +46,44 @@ constexpr int BKR = 32;        // real k per stage = one 128-byte swizzle row of
 constexpr int UMMA_K = 8;      // tf32
 constexpr int A_TILE = BM * BKR * 4;   // 16 KB
 
-static std::atomic<int> g_enabled{1};
+static int initial_mode() {
+  const char* e = getenv("MPDO_TC");      // 0 = off, 1 = on (default), 2 = on with the widest tiles
+  if (!e) return 1;
+  const int v = atoi(e);
+  return v < 0 ? 0 : (v > 2 ? 2 : v);
+}
+static std::atomic<int> g_enabled{initial_mode()};
+
+// Scratch for the prepared small operand: one grow-only device buffer per stream (consecutive launches on a stream
+// are ordered, so the buffer can be reused without synchronisation). A stream-ordered pool allocation per call was
+// measured to add occasional 50-350 ms stalls to a layer (pool growth while persistent kernels of other strands run).
+struct StreamScratch {
+  float* ptr = nullptr;
+  size_t bytes = 0;
+};
+static std::mutex g_scratch_mu;
+static std::unordered_map<cudaStream_t, StreamScratch> g_scratch;
+
+static float* stream_scratch(cudaStream_t st, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_scratch_mu);
+  StreamScratch& s = g_scratch[st];
+  if (s.bytes < bytes) {
+    if (s.ptr) {
+      cudaStreamSynchronize(st);
+      cudaFree(s.ptr);
+      s.ptr = nullptr;
+      s.bytes = 0;
+    }
+    size_t want = bytes < (size_t)(8 << 20) ? (size_t)(8 << 20) : bytes + bytes / 2;
+    if (cudaMalloc((void**)&s.ptr, want) != cudaSuccess) {
+      cudaGetLastError();
+      s.ptr = nullptr;
+      return nullptr;
+    }
+    s.bytes = want;
+  }
+  return s.ptr;
+}
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -377,14 +418,8 @@ int try_apply(const mpdo_contract_desc& d, const void* A, const void* B, void* C
 
   const int KR = 2 * d.K, NR = 2 * d.N;
   const size_t bElems = (size_t)d.batch * NR * KR;
-  float* scratch = nullptr;
-  cudaMemPool_t pool = eng::scratch_pool();
-  cudaError_t e = pool ? cudaMallocFromPoolAsync((void**)&scratch, 2 * bElems * sizeof(float), pool, st)
-                       : cudaMallocAsync((void**)&scratch, 2 * bElems * sizeof(float), st);
-  if (e != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
+  float* scratch = stream_scratch(st, 2 * bElems * sizeof(float));
+  if (!scratch) return 0;
   float *bh = scratch, *bl = scratch + bElems;
   {
     const long long total = (long long)d.batch * d.N * d.K;
@@ -392,10 +427,7 @@ int try_apply(const mpdo_contract_desc& d, const void* A, const void* B, void* C
     prep_b_kernel<<<gx, 256, 0, st>>>(d.K, d.N, d.batch, d.Bb, d.Bk, d.Bj, (const float2*)B, d.conjA, d.conjB, (float)d.alpha,
                                       bh, bl);
     int rc = check_launch("prep_b_kernel");
-    if (rc) {
-      cudaFreeAsync(scratch, st);
-      return rc;
-    }
+    if (rc) return rc;
   }
   // column tile: as wide as the result allows, but narrow enough that the accumulator chains stay short
   // (K / (4 NMAIN) k-steps per main accumulator: <= 32 up to K = 512)
@@ -408,10 +440,7 @@ int try_apply(const mpdo_contract_desc& d, const void* A, const void* B, void* C
   const bool ok = make_map(&mA, A, KR, d.M, d.batch, 2 * d.Ai.s0, 2 * d.Ab.s0, BM) &&
                   make_map(&mBh, bh, KR, NR, d.batch, KR, (long long)NR * KR, BN) &&
                   make_map(&mBl, bl, KR, NR, d.batch, KR, (long long)NR * KR, BN);
-  if (!ok) {
-    cudaFreeAsync(scratch, st);
-    return 0;
-  }
+  if (!ok) return 0;
   Params p;
   p.M = d.M;
   p.NR = NR;
@@ -430,7 +459,6 @@ int try_apply(const mpdo_contract_desc& d, const void* A, const void* B, void* C
     else
       rc = launch<64, 4>(mA, mBh, mBl, p, d.batch, st);
   }
-  cudaFreeAsync(scratch, st);
   return rc ? rc : 1;
 }
 
