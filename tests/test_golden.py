@@ -222,4 +222,8 @@ def test_host_api_matches_reference(name, cpu_model_prims):
         for ax in axes:
             # bond dimensions may differ by zero-weight directions (the reference re-pads a bond up to chi in the SVD
             # sweep and shrinks it in a reduced QR; the dense build pads with exact zeros instead) - same state
-            assert ax.startswith('bond') or got[ax] == want[ax], (ax, got, want)
+            # inner ("Kraus") dimensions may be smaller: gate operands are rewritten with the minimal number of Kraus
+            # operators (Circuit._compress_kraus; e.g. the 6 decay x dephasing operators of a noisy rotation are at most
+            # 4, and 1 on a chip preset whose rates are zero), an isometry on an index only traced against its conjugate
+            assert ax.startswith('bond') or got[ax] == want[ax] or (ax.startswith('I_') and got[ax] <= want[ax]), \
+                (ax, got, want)

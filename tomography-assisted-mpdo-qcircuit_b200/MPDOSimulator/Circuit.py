@@ -71,6 +71,24 @@ class TensorCircuit(QuantumCircuit):
         elif Bg > 1 and node.data.shape[0] != Bg:
             raise ValueError(f'batch mismatch: state has {node.data.shape[0]} circuits, gate has {Bg}')
 
+    @staticmethod
+    def _compress_kraus(G: tc.Tensor) -> tc.Tensor:
+        """G [B, (operator axes), K] -> the same channel written with at most d = (product of the operator axes)
+        Kraus operators. The Kraus index is only ever traced against its own conjugate (Circuit.py:240-242), so any
+        isometry on it leaves sum_g G_g rho G_g^h - and every later sweep / truncation, which see the index through
+        unitarily invariant quantities only - unchanged: G -> U S from the thin SVD of the d x K matrix. A noisy
+        single-qubit gate needs 4 operators instead of 6 (decay x dephasing), a fused pair of tomography CZs 16
+        instead of 256: the inner index of the site tensors shrinks by the same factor before any kernel runs."""
+        K = G.shape[-1]
+        B = G.shape[0]
+        d = G[0].numel() // K
+        if K <= d or os.environ.get('MPDO_NO_KRAUS_COMPRESSION'):
+            return G
+        U, S, _ = tc.linalg.svd(G.reshape(B, d, K).to(tc.complex128), full_matrices=False)
+        keep = max(1, int((S > 1e-15 * S[:, :1]).sum(dim=1).max()))
+        out = (U * S.unsqueeze(1))[:, :, :keep]
+        return out.reshape(*G.shape[:-1], keep).to(G.dtype)
+
     def _single_operand(self, gate: QuantumGate) -> Tuple[tc.Tensor, bool]:
         """[Bg, 2, 2, K] operand of a single-qubit gate and whether it carries noise (reference :141-155)."""
         noisy = (self.idealNoise or self.unified) and not gate.ideal
@@ -83,12 +101,15 @@ class TensorCircuit(QuantumCircuit):
 
         def build():
             Ub = U.reshape(-1, 2, 2)
-            return tc.einsum('nlm, ljk, bji -> bnimk', self.Noise.decayTensor, self.Noise.dephasingTensor,
-                             Ub).reshape(Ub.shape[0], 2, 2, -1)
+            return self._compress_kraus(tc.einsum('nlm, ljk, bji -> bnimk', self.Noise.decayTensor,
+                                                  self.Noise.dephasingTensor, Ub).reshape(Ub.shape[0], 2, 2, -1))
 
+        # the second value is truthy for a noisy gate and carries the number of Kraus operators of the reference's own
+        # construction (2 decay x 3 dephasing), which DenseNode.ref_inner keeps track of
+        kref = int(self.Noise.decayTensor.shape[-1] * self.Noise.dephasingTensor.shape[-1])
         if gate.variational:
-            return build(), True
-        return self.noiseTensorDict.setdefault(gate.name, build()), True
+            return build(), kref
+        return self.noiseTensorDict.setdefault(gate.name, build()), kref
 
     def _double_operand(self, gate: QuantumGate, _oqs: List[int]) -> Tuple[tc.Tensor, bool]:
         """[Bg, 2, 2, 2, 2, K] operand in (lo, hi) qubit order and whether it adds an inner index (:84-99)."""
@@ -101,10 +122,12 @@ class TensorCircuit(QuantumCircuit):
             base = G.reshape(-1, 2, 2, 2, 2)
             G = self.noiseTensorDict.setdefault(
                 gate.name, tc.einsum('ijklp, bklmn -> bijmnp', self.Noise.dpCTensor2, base))
+            noisy = int(G.shape[-1])          # truthy, and the reference's Kraus count (see _single_operand)
         elif self.realNoise:
             if G.dim() != 5:
                 raise ValueError('realNoise mode needs a (2,2,2,2,K) two-qubit gate tensor (CZEXP / CPEXP).')
             G = G.unsqueeze(0)
+            noisy = int(G.shape[-1])
         else:
             if G.shape[-4:] != (2, 2, 2, 2):
                 raise ValueError(f'two-qubit gate tensor of shape {tuple(G.shape)} cannot be applied without a noise axis')
@@ -154,12 +177,14 @@ class TensorCircuit(QuantumCircuit):
         """Theta = T_lo . T_hi . G, split back with the reference rank rule; the noise index goes to `hi`.
         The kept rank (batch maximum) is recorded in last_stats['split_ranks'][layer index]."""
         eng = self._engine()
+        before = _qNodes[hi].nominal_inner()
         _qNodes[lo].data, _qNodes[hi].data = eng.split_2q(_qNodes[lo].data, _qNodes[hi].data, G, GLOBAL_MINIMUM)
         if _tag is not None:
             self.last_stats.setdefault('split_ranks', {})[_tag] = int(_qNodes[lo].data.shape[4])
         _qNodes[lo].has_right = True
         _qNodes[hi].has_left = True
         if noisy:
+            _qNodes[hi].ref_inner = before * int(noisy)
             _qNodes[hi].has_inner = True
 
     # Largest composite Kraus count a fused pair may carry (two tomography CZs: 16 x 16).
@@ -221,8 +246,9 @@ class TensorCircuit(QuantumCircuit):
                     M[q] = U @ M[q]
             tot = tc.einsum('bpqtvg, btu, bvw, buwxyh -> bpqxygh', Bt.to(tc.complex128), M[lo], M[hi],
                             A.to(tc.complex128))
-            tot = tot.reshape(*tot.shape[:5], -1)
-            out.append(('fused', lo, hi, tot, noisyA or noisyB, chain[j][0]))
+            tot = self._compress_kraus(tot.reshape(*tot.shape[:5], -1))
+            kref = (int(noisyA) or 1) * (int(noisyB) or 1) if (noisyA or noisyB) else False
+            out.append(('fused', lo, hi, tot, kref, chain[j][0]))
             i = j + 1
         return out
 
@@ -234,8 +260,10 @@ class TensorCircuit(QuantumCircuit):
         eng = self._engine()
         for q in _oqs:
             self._match_batch(_qNodes[q], G.shape[0])
+            before = _qNodes[q].nominal_inner()
             _qNodes[q].data = eng.absorb_1q(_qNodes[q].data, G)
             if noisy:
+                _qNodes[q].ref_inner = before * int(noisy)
                 _qNodes[q].has_inner = True
 
     def _add_gate(self, _qubits: List[DenseNode], _layer_num: int, _oqs: List[int], _gate: Optional = None):
@@ -415,7 +443,8 @@ class TensorCircuit(QuantumCircuit):
                 parts.append(node.data)
             stacked.append(parts[0] if M == 1 else tc.cat(parts, dim=0))
         rel = {q: j for j, q in enumerate(qubits0)}
-        flags = [dict(l=state[q].has_left, r=state[q].has_right, i=state[q].has_inner) for q in qubits0]
+        flags = [dict(l=state[q].has_left, r=state[q].has_right, i=state[q].has_inner, k=1) for q in qubits0]
+        nominal = [[state[qs[j]].nominal_inner() for j in range(len(qubits0))] for qs, _ in members]
         ranks = {}
         for t, st in enumerate(steps0):
             Gs = [sts[t][-3 if st[0] == '2q' else -2] for _, sts in members]
@@ -427,12 +456,14 @@ class TensorCircuit(QuantumCircuit):
             if st[0] == '1q':
                 j = rel[st[1]]
                 stacked[j] = eng.absorb_1q(stacked[j], G)
-                flags[j]['i'] = flags[j]['i'] or st[3]
+                flags[j]['i'] = flags[j]['i'] or bool(st[3])
+                flags[j]['k'] *= int(st[3]) or 1
             else:
                 jl, jh = rel[st[1]], rel[st[2]]
                 stacked[jl], stacked[jh] = eng.split_2q(stacked[jl], stacked[jh], G, GLOBAL_MINIMUM)
                 flags[jl]['r'] = flags[jh]['l'] = True
-                flags[jh]['i'] = flags[jh]['i'] or st[4]
+                flags[jh]['i'] = flags[jh]['i'] or bool(st[4])
+                flags[jh]['k'] *= int(st[4]) or 1
                 per_row = getattr(eng.tls, 'last_ranks', None)
                 for m, (_, sts) in enumerate(members):
                     tag = sts[t][5]
@@ -446,6 +477,8 @@ class TensorCircuit(QuantumCircuit):
                 node = state[q]
                 node.data = stacked[j] if M == 1 else stacked[j][m * Bmax:(m + 1) * Bmax]
                 node.has_left, node.has_right, node.has_inner = flags[j]['l'], flags[j]['r'], flags[j]['i']
+                if flags[j]['k'] > 1:
+                    node.ref_inner = nominal[m][j] * flags[j]['k']
 
     def forward(self, state: List[DenseNode]):
         self.evolve(state)

@@ -86,7 +86,13 @@ def svdKappa_left2right(_qubits: List[DenseNode], max_singular_values: Optional[
     eng = _engine_of(_qubits)
     todo = []
     for q in _qubits:
-        if max_singular_values is not None and (not q.has_inner or q.data.shape[3] <= max_singular_values):
+        # the reference skips a site by its own inner dimension (:176-181), which counts redundant Kraus operators
+        # that the dense build never materialises (DenseNode.ref_inner)
+        if max_singular_values is not None and (not q.has_inner or q.nominal_inner() <= max_singular_values):
+            continue
+        if (max_truncation_err is None and max_singular_values is not None and q.has_inner
+                and q.data.shape[3] <= max_singular_values):
+            q.ref_inner = None      # nothing to cut: T <- U S would only rotate the inner index (a gauge change)
             continue
         if not q.has_inner:
             raise ValueError(f'Axis name I_{q.index} not found')
@@ -113,12 +119,14 @@ def svdKappa_left2right(_qubits: List[DenseNode], max_singular_values: Optional[
             if len(members) == 1:
                 q = members[0]
                 q.data, _ = eng.kappa_truncate(q.data, max_singular_values, max_truncation_err)
+                q.ref_inner = None
                 return
             B = members[0].data.shape[0]
             out, _ = eng.kappa_truncate(torch.cat([q.data for q in members], dim=0), max_singular_values,
                                         max_truncation_err)
             for m, q in enumerate(members):
                 q.data = out[m * B:(m + 1) * B]
+                q.ref_inner = None
         return task
 
     device = _qubits[0].data.device
@@ -130,7 +138,7 @@ def svdKappa_left2right(_qubits: List[DenseNode], max_singular_values: Optional[
 
 
 def _needs_kappa(q: DenseNode, kappa: Optional[int]):
-    return not (kappa is not None and (not q.has_inner or q.data.shape[3] <= kappa))
+    return not (kappa is not None and (not q.has_inner or q.nominal_inner() <= kappa))
 
 
 def truncateLayer(_qubits: List[DenseNode], chi: Optional[int] = None, kappa: Optional[int] = None,
@@ -168,9 +176,13 @@ def truncateLayer(_qubits: List[DenseNode], chi: Optional[int] = None, kappa: Op
             if not q.has_inner:
                 raise ValueError(f'Axis name I_{q.index} not found')
             q.data, _ = eng.kappa_truncate(q.data, kappa, max_truncation_err)
+            q.ref_inner = None
 
     def launch(q):
         if not _needs_kappa(q, kappa):
+            return
+        if max_truncation_err is None and kappa is not None and q.data.shape[3] <= kappa:
+            q.ref_inner = None
             return
         ev = torch.cuda.Event()
         ev.record(main)

@@ -37,6 +37,11 @@ class DenseNode:
         self.index = index
         self.name = name if name is not None else f'qubit_{index}'
         self.has_left, self.has_right, self.has_inner = has_left, has_right, has_inner
+        # Inner dimension the REFERENCE node would have (None: same as data.shape[3]). Gate operands are applied with
+        # the minimal number of Kraus operators (Circuit._compress_kraus), but the reference decides whether a site
+        # takes part in the inner-index truncation by dim(I_k) > kappa on its own, redundant, dimension
+        # (TNNOptimizer.py:176-181), so that number is carried along.
+        self.ref_inner = None
 
     # --- reference-node look-alikes -------------------------------------------------------------
     def _axes(self):
@@ -88,8 +93,13 @@ class DenseNode:
     def shape(self):
         return tuple(self.tensor.shape)
 
+    def nominal_inner(self) -> int:
+        return int(self.data.shape[3]) if self.ref_inner is None else int(self.ref_inner)
+
     def copy(self):
-        return DenseNode(self.data.clone(), self.index, self.name, self.has_left, self.has_right, self.has_inner)
+        node = DenseNode(self.data.clone(), self.index, self.name, self.has_left, self.has_right, self.has_inner)
+        node.ref_inner = self.ref_inner
+        return node
 
     def __repr__(self):
         return f'DenseNode({self.name}, axes={self.axis_names}, data={tuple(self.data.shape)}, {self.data.dtype})'
