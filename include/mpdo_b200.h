@@ -216,6 +216,12 @@ int mpdo_trim_pools(void);
  * workload outgrew the pre-grown block). Either pointer may be NULL. */
 int mpdo_pool_stats(int64_t* reservedBytes, int64_t* reservedHighBytes);
 
+/* Test hook for the bounded device-wide barrier of the persistent factorisation kernels: launches two CTAs of which
+ * one never arrives. The waiting CTA gives up after a short poll limit and traps, so the call returns a CUDA error
+ * (and the context is unusable afterwards: call it from a throw-away process). A barrier that times out in
+ * production (limit 2^24 polls) fails the same way - loudly - rather than returning a half-updated factorisation. */
+int mpdo_debug_barrier_timeout(void* stream);
+
 /* Library / device information. */
 int mpdo_version(void);
 const char* mpdo_last_error(void);

@@ -26,3 +26,24 @@ def test_long_range_gates(cuda_prims, dtype, tol):
 def test_chi_formats_and_cp_tomography(cuda_prims, tmp_path, dtype, tol):
     """.npz ('chi') and .mat ('exp') process matrices, CPEXP gates from chiFileDict['CP']."""
     ec.check_chi_formats_and_cp(dtype, 'cuda:0', tol, str(tmp_path))
+
+
+def test_barrier_timeout_fails_loudly(cuda_prims):
+    """The device-wide barrier of the persistent Cholesky / Jacobi kernels is bounded: a CTA that waits too long
+    traps, and the library call reports a CUDA error instead of returning a half-updated factorisation. Run in a
+    throw-away process (a trap leaves the CUDA context unusable)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path[:0] = [%r, %r]\n"
+        "import torch; torch.cuda.init()\n"
+        "from MPDOSimulator._engine import lib\n"
+        "h = lib.load()\n"
+        "rc = h.mpdo_debug_barrier_timeout(None)\n"
+        "print('rc', rc, (h.mpdo_last_error() or b'').decode())\n"
+        "sys.exit(0 if rc != 0 else 7)\n" % (root, os.path.join(root, 'tomography-assisted-mpdo-qcircuit_b200')))
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    print(out.stdout.strip(), out.stderr.strip()[-200:])
+    assert out.returncode == 0, 'a barrier time-out must surface as an error'

@@ -66,6 +66,7 @@ SYMBOLS = {
     'mpdo_timing_enable': (C.c_int, [C.c_int]),
     'mpdo_timing_summary': (C.c_int, [C.c_int, C.c_double] + [C.POINTER(C.c_double)] * 3 + [C.POINTER(C.c_int64)] +
                             [C.POINTER(C.c_double)] * 2),
+    'mpdo_debug_barrier_timeout': (C.c_int, [C.c_void_p]),
     'mpdo_version': (C.c_int, []),
     'mpdo_last_error': (C.c_char_p, []),
     'mpdo_device_info': (C.c_int, [C.POINTER(C.c_int)] * 4),

@@ -74,7 +74,11 @@ __device__ __forceinline__ long long map_idx(const mpdo_idxmap& m, int i) {
 #ifdef __CUDACC__
 // Device-wide barrier between the CTAs that work on one matrix (grid.x of them; the kernel is launched
 // cooperatively, so they are co-resident). `bar` only ever increases: round `phase` completes at (phase+1)*nblk.
-__device__ __forceinline__ void matrix_barrier(unsigned* bar, unsigned nblk, unsigned& phase, int* errflag) {
+// A CTA that does not see the others arrive within `limit` polls (seconds at the default: never expected, it means the
+// CTAs are not co-resident or one of them died) sets *errflag and TRAPS: the kernel aborts and every later CUDA call of
+// the process reports the failure, instead of a factorisation that silently used half-updated data.
+__device__ __forceinline__ void matrix_barrier(unsigned* bar, unsigned nblk, unsigned& phase, int* errflag,
+                                               unsigned limit = 1u << 24) {
   __syncthreads();
   if (threadIdx.x == 0) {
     // arrive: release at gpu scope (cumulative over the CTA's writes ordered by the bar.sync above), no return value
@@ -84,9 +88,10 @@ __device__ __forceinline__ void matrix_barrier(unsigned* bar, unsigned nblk, uns
     for (;;) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
       if (seen >= target) break;
-      if (++spins > (1u << 24)) {  // ~seconds: never expected; refuse to hang the device
+      if (++spins > limit) {  // refuse to hang the device, and refuse to continue with inconsistent data
         *errflag = 1;
-        break;
+        __threadfence_system();
+        __trap();
       }
     }
   }

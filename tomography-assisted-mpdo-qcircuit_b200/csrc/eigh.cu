@@ -48,9 +48,9 @@ struct CholArgs {
 
 constexpr int CHOL_THREADS = 256;
 
-// shared-memory layout: Ls[R][n] | prow[n] | dl[R] (double) | chosen[R] (int) | piv[n] (int) | pad | Ws[R][n]
+// shared-memory layout: Ls[R][n] | prow[n] | grow[R] | dl[R] (double) | chosen[R] (int) | piv[n] (int) | pad | Ws[R][n]
 __host__ __device__ inline size_t chol_ws_offset(int n, int R) {
-  size_t off = ((size_t)R * n + n) * sizeof(double2) + (size_t)R * 12 + (size_t)n * 4;
+  size_t off = ((size_t)R * n + n + R) * sizeof(double2) + (size_t)R * 12 + (size_t)n * 4;
   return (off + 15) & ~(size_t)15;
 }
 
@@ -66,7 +66,9 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   double2* Ls = csm;                          // [R][n]: own rows of L, column index = step
   double2* prow = Ls + (size_t)R * n;         // [n]: pivot row of the current step
-  double* dl = reinterpret_cast<double*>(prow + n);   // [R]: remaining diagonal of own rows
+  double2* grow = prow + n;                   // [R]: G[pivot, own rows] of the current step (one coalesced load per
+                                              // step; read per row from global memory it cost ~700 cycles per row)
+  double* dl = reinterpret_cast<double*>(grow + R);   // [R]: remaining diagonal of own rows
   int* chosen = reinterpret_cast<int*>(dl + R);       // [R]
   int* pivRow = chosen + R;                             // [n]: pivot row of every step (inverse only)
   double2* Ws = reinterpret_cast<double2*>(reinterpret_cast<char*>(csm) + chol_ws_offset(n, R));   // [R][n]: own
@@ -226,6 +228,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs p) {
       rank = k;
       break;
     }
+    for (int r = tid; r < rows; r += blockDim.x) grow[r] = G[(long long)pg * n + row0 + r];
     __syncthreads();
     CHOL_MARK(3);
     const double piv = sqrt(pval), inv = 1.0 / piv;
@@ -255,7 +258,7 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs p) {
           ar += __shfl_xor_sync(0xffffffffu, ar, o);
           ai += __shfl_xor_sync(0xffffffffu, ai, o);
         }
-        const double2 g = G[(long long)pg * n + i];   // G[i,p] = conj(G[p,i])
+        const double2 g = grow[r];   // G[p,i]; G[i,p] is its conjugate
         out.x = (g.x - ar) * inv;
         out.y = (-g.y - ai) * inv;
         dnew = fmax(dold - (out.x * out.x + out.y * out.y), 0.0);
@@ -516,7 +519,10 @@ static int chol_launch(int batch, int n, const void* G, void* Y, void* X, void* 
     a.slots = (double2*)slotsBase + (long long)b0 * 2 * C * (n + 1);
     a.info = info + 4LL * b0;
     a.cluster = cluster ? 1 : 0;
-    TimedLaunch timed(2, 0.0, 0.0, st);
+    // algorithmic work (SURVEY 8d convention, 8 real flops per complex multiply-add): n^3 / 3 for the factor and the
+    // same again for the left inverse
+    const double cflops = 8.0 * nb * ((double)n * n * n / 3.0) * (X ? 2.0 : 1.0);
+    TimedLaunch timed(2, cflops, 16.0 * nb * (double)n * n * (X ? 3.0 : 2.0), st);
     if (cluster) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(C, nb);

@@ -270,6 +270,26 @@ extern "C" int mpdo_timing_summary(int cls, double minFlops, double* seconds, do
   return 0;
 }
 
+// Debug / test hook: a two-CTA launch in which CTA 1 never arrives at the device-wide barrier, with a short poll limit.
+// The waiting CTA must trap (see matrix_barrier); the call returns the resulting CUDA error.
+__global__ void barrier_timeout_kernel(unsigned* bar, int* flag) {
+  unsigned phase = 0;
+  if (blockIdx.x == 0) mpdo::matrix_barrier(bar, 2u, phase, flag, 1u << 12);
+}
+
+extern "C" int mpdo_debug_barrier_timeout(void* stream) {
+  using namespace mpdo;
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned* bar = nullptr;
+  MPDO_CUDA(cudaMalloc((void**)&bar, 16));
+  MPDO_CUDA(cudaMemsetAsync(bar, 0, 16, st));
+  barrier_timeout_kernel<<<2, 32, 0, st>>>(bar, reinterpret_cast<int*>(bar) + 2);
+  int rc = check_launch("barrier_timeout_kernel");
+  if (rc) return rc;
+  MPDO_CUDA(cudaStreamSynchronize(st));   // returns the launch failure raised by the trap
+  return 0;
+}
+
 extern "C" int mpdo_version(void) { return 100; }
 extern "C" const char* mpdo_last_error(void) { return mpdo::g_err; }
 extern "C" int64_t mpdo_launch_count(void) { return mpdo::g_launches.load(); }

@@ -701,8 +701,10 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
   if (const char* e = getenv("MPDO_JACOBI_G")) G = atoi(e) == 8 ? 8 : (atoi(e) == 16 ? 16 : 32);   // tuning knob
   const int ppw = 32 / G;
   const unsigned threads = 32u * (unsigned)((b + ppw - 1) / ppw);
+  // algorithmic work of the decomposition this launch is (part of): the SURVEY 8d SVD count 4 (6 m n^2 + 20 n^3)
+  // for n rows of length m per matrix (an eigen-decomposition has m = n); multi-launch sweeps report it once
   auto launch = [&](dim3 grid) {
-    TimedLaunch timed(1, 0.0, 0.0, st);
+    TimedLaunch timed(1, 4.0 * batch * (6.0 * m * (double)n * n + 20.0 * (double)n * n * n), 32.0 * batch * (double)n * m, st);
     if (G == 8)
       jacobi_kernel<8><<<grid, threads, smem, st>>>(a, (double2*)Y);
     else if (G == 16)
@@ -775,7 +777,7 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
         ac.rank = rank ? rank + (long long)b0 * rankStride : nullptr;
         double2* Yc = (double2*)Y + (long long)b0 * batchStride;
         void* args[] = {(void*)&ac, (void*)&Yc};
-        TimedLaunch timed(1, 0.0, 0.0, st);
+        TimedLaunch timed(1, 4.0 * nbat * (6.0 * m * (double)n * n + 20.0 * (double)n * n * n), 32.0 * nbat * (double)n * m, st);
         cudaError_t e;
         if (P > 1) {
           e = cudaLaunchCooperativeKernel(fn, dim3((unsigned)P, nbat), dim3(nthreads), args, smem, st);
