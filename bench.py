@@ -433,6 +433,7 @@ def b200_arm(args):
                 'largest_seconds': mxs.value, 'largest_flops': mxf.value}
 
     t_c32, t_c64, t_big32, t_big64 = timing(0), timing(3), timing(0, 2e9), timing(3, 2e9)
+    t_tc, t_bigtc = timing(4), timing(4, 2e9)            # tcgen05 / TMA applies (csrc/tc_apply.cu)
     t_jacobi, t_chol = timing(1), timing(2)
 
     def merged(a, b):   # fp32- and fp64-accumulated contraction launches together
@@ -441,7 +442,7 @@ def b200_arm(args):
         out['largest_seconds'], out['largest_flops'] = big['largest_seconds'], big['largest_flops']
         return out
 
-    t_contract, t_big = merged(t_c32, t_c64), merged(t_big32, t_big64)
+    t_contract, t_big = merged(merged(t_c32, t_c64), t_tc), merged(merged(t_big32, t_big64), t_bigtc)
     lib.mpdo_timing_enable(0)
 
     # ---- e2e: host buffers in, host buffers out, every step -------------------------------------------
@@ -538,8 +539,9 @@ def b200_arm(args):
         ct, cf = max(t_contract['seconds'], 1e-30), t_contract['flops']
         roof = {
             'bound': 'tensor',
-            'kernel': 'contract_kernel (batched complex contraction: fp64-accumulated launches on DMMA m8n8k4 tensor '
-                      'tiles, complex64 applies on FP32 FFMA tiles), all launches',
+            'kernel': 'contraction kernels, all launches: tc_apply_kernel (complex64 applies: tcgen05.mma kind::tf32 3xTF32, '
+                      'TMA tiles, TMEM accumulators) + contract_kernel (fp64-accumulated Gram matrices and cores on DMMA '
+                      'm8n8k4 tiles; short / strided complex64 products on FP32 FFMA tiles)',
             'achieved': cf / ct / 1e12, 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': cf / ct / 1e12 / peak_tf,
             'traffic': None, 'peak_source': peak_src,
             'launches_timed': t_contract['launches'], 'kernel_seconds': ct, 'share_of_step_device_time': None,
@@ -579,19 +581,30 @@ def b200_arm(args):
                     'pipe_peak_TFLOP/s': peak}
 
         roof['by_pipe'] = {'fp64_accumulated (DMMA m8n8k4 tiles)': pipe(t_c64, t_big64, fp64_peak),
-                           'fp32 (FFMA tiles)': pipe(t_c32, t_big32, fp32_peak)}
+                           'fp32 (FFMA tiles)': pipe(t_c32, t_big32, fp32_peak),
+                           # algorithmic rate; the tile executes 3 tf32 MMAs per product (3xTF32), so the tensor pipe
+                           # is 3x busier than this figure says. Pipe peak taken as half the measured bf16 peak.
+                           'tcgen05 kind::tf32 3xTF32 (TMA + TMEM)': pipe(t_tc, t_bigtc, peak_tf / 2)}
         jt = max(t_jacobi['seconds'], 1e-30)
         ht = max(t_chol['seconds'], 1e-30)
         roof['share_of_step_device_time'] = ct / (ct + jt + ht)
+        roof['dominant_by_device_time'] = ('factorisation kernels (see factorisation_kernels): after the work reductions '
+                                           'of round 2 the contractions are a few per cent of the layer')
         dominant = {
             'jacobi': {'kernel': 'jacobi_kernel / jacobi_persistent_kernel (one-sided Jacobi on fp64 rows in shared memory)',
                        'launches': t_jacobi['launches'], 'kernel_seconds': jt,
                        'avg_launch_us': 1e6 * jt / max(t_jacobi['launches'], 1),
-                       'share_of_timed_device_seconds': jt / (ct + jt + ht)},
+                       'share_of_timed_device_seconds': jt / (ct + jt + ht),
+                       'algorithmic_TFLOP/s': t_jacobi['flops'] / jt / 1e12,
+                       'frac': t_jacobi['flops'] / jt / 1e12 / fp64_peak, 'peak': fp64_peak,
+                       'flops_convention': 'SURVEY 8d SVD count 4 (6 m n^2 + 20 n^3) per decomposition'},
             'cholesky': {'kernel': 'chol_kernel (rank-revealing pivoted Cholesky, rows of L resident in shared memory)',
                          'launches': t_chol['launches'], 'kernel_seconds': ht,
                          'avg_launch_us': 1e6 * ht / max(t_chol['launches'], 1),
-                         'share_of_timed_device_seconds': ht / (ct + jt + ht)},
+                         'share_of_timed_device_seconds': ht / (ct + jt + ht),
+                         'algorithmic_TFLOP/s': t_chol['flops'] / ht / 1e12,
+                         'frac': t_chol['flops'] / ht / 1e12 / fp64_peak, 'peak': fp64_peak,
+                         'flops_convention': '8 n^3 / 3 for the factor + the same for the left inverse'},
             'bound': 'latency: one device-wide barrier per tournament round / pivot step on 1-64 SMs per matrix '
                      '(ncu: profiles/)',
             'note': 'kernel seconds are summed over concurrent streams, so they can exceed the wall time of the step',

@@ -329,6 +329,148 @@ __global__ void __launch_bounds__(CHOL_THREADS) chol_kernel(CholArgs p) {
   if (c == 0 && tid == 0) info[0] = rank;
 }
 
+// ---- small matrices (n <= CS_MAXN): one CTA, thread per row ---------------------------------------------------
+// The general kernel above gives one WARP to a row and reduces every dot product with 64-bit shuffles; with the 8 rows
+// per warp of a 64 x 64 matrix that is ~9000 cycles per pivot step (0.28 ms per factorisation, and an MPDO layer at
+// chi = 64 needs ~30 of them one after the other). Here a THREAD owns a row: L is kept transposed in shared memory
+// (LT[j][i] = L[i,j], odd leading dimension), so the threads of a warp read consecutive entries of column j while
+// every thread walks its own dot product sequentially - no shuffle reductions, no warp-per-row serialisation. The
+// rows of the left inverse W = L11^-1 are computed at the same time by a second group of threads (thread per column).
+// Same pivot order (largest remaining diagonal, ties to the lowest row), stop rule and outputs as chol_kernel.
+constexpr int CS_MAXN = 80;       // LT and W in shared memory: 2 n (n + 1) 16 B = 207 KB at n = 80
+constexpr int CS_ROWT = 96;       // threads 0..95: rows;  96..191: columns of the inverse
+constexpr int CS_THREADS = 192;
+
+__global__ void __launch_bounds__(CS_THREADS) chol_small_kernel(CholArgs p) {
+  extern __shared__ double2 csm[];
+  __shared__ double sBestV[CS_ROWT / 32];
+  __shared__ int sBestI[CS_ROWT / 32];
+  __shared__ int sPiv[CS_MAXN];
+  const int n = p.n, ld = n | 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, bidx = blockIdx.y;
+  const double2* G = p.G + (long long)bidx * n * n;
+  double2* Y = p.Y + (long long)bidx * n * n;
+  double2* X = p.X ? p.X + (long long)bidx * n * n : nullptr;
+  double2* LT = csm;                                   // [n][ld]: LT[j * ld + i] = L[i, j]
+  double2* Wm = LT + (size_t)n * ld;                   // [n][ld]: Wm[j * ld + c] = W[j, c] (pivot order), if X
+  double2* prow = (X ? Wm : LT) + (size_t)n * ld;      // [n]: L[pivot, 0..k)
+  double2* grow = prow + n;                            // [n]: G[pivot, :]
+  const bool rowThread = tid < CS_ROWT;
+  const int i = tid;                                   // row owned by a row thread
+  const int c = tid - CS_ROWT;                         // inverse column owned by the other threads
+  double d = (rowThread && i < n) ? G[(long long)i * n + i].x : -1.0;
+  bool chosen = !(rowThread && i < n);
+  double thresh = 0;
+  int rank = n;
+  for (int k = 0; k < n; ++k) {
+    if (rowThread) {   // largest remaining diagonal, ties to the lowest row
+      double v = chosen ? -1.0 : d;
+      int vi = chosen ? 0x7fffffff : i;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+        if (ov > v || (ov == v && oi < vi)) {
+          v = ov;
+          vi = oi;
+        }
+      }
+      if (lane == 0) {
+        sBestV[warp] = v;
+        sBestI[warp] = vi;
+      }
+    }
+    __syncthreads();
+    double pval = -1.0;
+    int pg = 0x7fffffff;
+#pragma unroll
+    for (int w = 0; w < CS_ROWT / 32; ++w) {
+      const double v = sBestV[w];
+      const int vi = sBestI[w];
+      if (v > pval || (v == pval && vi < pg)) {
+        pval = v;
+        pg = vi;
+      }
+    }
+    if (k == 0) thresh = p.rel * pval;
+    if (pg == 0x7fffffff || !(pval > thresh) || !(pval > 0.0)) {   // the same data in every thread
+      rank = k;
+      break;
+    }
+    for (int j = tid; j < k; j += CS_THREADS) prow[j] = LT[(size_t)j * ld + pg];
+    if (!rowThread)
+      for (int r = c; r < n; r += CS_THREADS - CS_ROWT) grow[r] = G[(long long)pg * n + r];
+    if (tid == 0) sPiv[k] = pg;
+    __syncthreads();
+    const double piv = sqrt(pval), inv = 1.0 / piv;
+    if (rowThread) {
+      if (i < n) {
+        double2 out = make_double2(0.0, 0.0);
+        if (i == pg) {
+          out.x = piv;
+          chosen = true;
+        } else if (!chosen) {
+          double ar0 = 0, ai0 = 0, ar1 = 0, ai1 = 0;   // sum_j L[i,j] conj(L[p,j]), two chains for ILP
+          int j = 0;
+          for (; j + 1 < k; j += 2) {
+            const double2 a0 = LT[(size_t)j * ld + i], b0 = prow[j];
+            const double2 a1 = LT[(size_t)(j + 1) * ld + i], b1 = prow[j + 1];
+            ar0 = fma(a0.x, b0.x, fma(a0.y, b0.y, ar0));
+            ai0 = fma(a0.y, b0.x, fma(-a0.x, b0.y, ai0));
+            ar1 = fma(a1.x, b1.x, fma(a1.y, b1.y, ar1));
+            ai1 = fma(a1.y, b1.x, fma(-a1.x, b1.y, ai1));
+          }
+          if (j < k) {
+            const double2 a0 = LT[(size_t)j * ld + i], b0 = prow[j];
+            ar0 = fma(a0.x, b0.x, fma(a0.y, b0.y, ar0));
+            ai0 = fma(a0.y, b0.x, fma(-a0.x, b0.y, ai0));
+          }
+          const double2 g = grow[i];                   // G[p,i]; G[i,p] is its conjugate
+          out.x = (g.x - (ar0 + ar1)) * inv;
+          out.y = (-g.y - (ai0 + ai1)) * inv;
+          d = fmax(d - (out.x * out.x + out.y * out.y), 0.0);
+        }
+        LT[(size_t)k * ld + i] = out;
+        Y[(long long)k * n + i] = make_double2(out.x, -out.y);
+      }
+    } else if (X && c <= k) {
+      // row k of W = L11^-1 (pivot order):  W[k,k] = 1/piv,  W[k,c] = -(sum_{c<=j<k} L[p_k,j] W[j,c]) / piv
+      double2 w = make_double2(inv, 0.0);
+      if (c < k) {
+        double ar0 = 0, ai0 = 0, ar1 = 0, ai1 = 0;
+        int j = c;
+        for (; j + 1 < k; j += 2) {
+          const double2 a0 = prow[j], b0 = Wm[(size_t)j * ld + c];
+          const double2 a1 = prow[j + 1], b1 = Wm[(size_t)(j + 1) * ld + c];
+          ar0 = fma(a0.x, b0.x, fma(-a0.y, b0.y, ar0));
+          ai0 = fma(a0.x, b0.y, fma(a0.y, b0.x, ai0));
+          ar1 = fma(a1.x, b1.x, fma(-a1.y, b1.y, ar1));
+          ai1 = fma(a1.x, b1.y, fma(a1.y, b1.x, ai1));
+        }
+        if (j < k) {
+          const double2 a0 = prow[j], b0 = Wm[(size_t)j * ld + c];
+          ar0 = fma(a0.x, b0.x, fma(-a0.y, b0.y, ar0));
+          ai0 = fma(a0.x, b0.y, fma(a0.y, b0.x, ai0));
+        }
+        w.x = -(ar0 + ar1) * inv;
+        w.y = -(ai0 + ai1) * inv;
+      }
+      Wm[(size_t)k * ld + c] = w;
+      X[(long long)k * n + (c == k ? pg : sPiv[c])] = w;
+    }
+    // no barrier here: the next step's pivot search only touches registers, and its first barrier orders this
+    // step's shared-memory writes before anybody reads them
+  }
+  for (long long idx = (long long)rank * n + tid; idx < (long long)n * n; idx += CS_THREADS)
+    Y[idx] = make_double2(0.0, 0.0);                    // rows of Y beyond the rank are zero
+  if (tid == 0) p.info[4LL * bidx] = rank;
+}
+
+static size_t chol_small_smem(int n, bool inverse) {
+  const size_t ld = (size_t)(n | 1);
+  return ((inverse ? 2 : 1) * (size_t)n * ld + 2 * (size_t)n) * sizeof(double2);
+}
+
 static size_t chol_smem(int n, int R, bool inverse) {
   return chol_ws_offset(n, R) + (inverse ? (size_t)R * n * sizeof(double2) : 0);
 }
@@ -487,6 +629,40 @@ static int chol_launch(int batch, int n, const void* G, void* Y, void* X, void* 
                        int* info, double rel, cudaStream_t st, int* rcOut) {
   int R = 0, C = 0, chunk = 0;
   *rcOut = 0;
+  static const bool noSmall = getenv("MPDO_CHOL_NOSMALL") != nullptr;   // A/B knob: always the general kernel
+  if (n <= CS_MAXN && batch <= 65535 && !noSmall) {
+    static bool configured = false;
+    if (!configured) {
+      if (cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)chol_small_smem(CS_MAXN, true)) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+      }
+      configured = true;
+    }
+    cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int) * 4 * (size_t)batch, st);
+    if (e == cudaSuccess && X) e = cudaMemsetAsync(X, 0, sizeof(double2) * (size_t)batch * n * n, st);
+    if (e != cudaSuccess) {
+      snprintf(g_err, sizeof(g_err), "chol memset: %s", cudaGetErrorString(e));
+      *rcOut = (int)e;
+      return 0;
+    }
+    CholArgs a;
+    a.n = n;
+    a.R = n;
+    a.rel = rel;
+    a.G = (const double2*)G;
+    a.Y = (double2*)Y;
+    a.X = (double2*)X;
+    a.slots = nullptr;
+    a.info = info;
+    a.cluster = 0;
+    const double cflops = 8.0 * batch * ((double)n * n * n / 3.0) * (X ? 2.0 : 1.0);
+    TimedLaunch timed(2, cflops, 16.0 * batch * (double)n * n * (X ? 3.0 : 2.0), st);
+    chol_small_kernel<<<dim3(1, batch), CS_THREADS, chol_small_smem(n, X != nullptr), st>>>(a);
+    *rcOut = check_launch("chol_small_kernel");
+    return 0;
+  }
   bool cluster = false;
   int optin = 0, dev = 0;
   if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
