@@ -478,17 +478,24 @@ static size_t chol_smem(int n, int R, bool inverse) {
 // rows per CTA / CTAs per matrix and the number of matrices one launch can hold co-resident (a batch beyond that is
 // factorised in consecutive launches of `chunk` matrices), or false when not even one matrix can be scheduled
 static bool chol_plan(int batch, int n, bool inverse, int* Rout, int* Cout, int* chunkOut) {
+  // one-time set-up behind a mutex: strands call this from a dozen host threads at once, and a thread must not see
+  // the cached attribute before the kernel's shared-memory limit has actually been raised (observed as a sporadic
+  // "chol_kernel: invalid argument" on the first layer of a process)
+  static std::mutex initMu;
   static int smemMax = 0, sms = 0, coop = 0;
-  if (!smemMax) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return false;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024) != cudaSuccess) {
-      cudaGetLastError();
-      smemMax = 0;
-      return false;
+  {
+    std::lock_guard<std::mutex> lk(initMu);
+    if (!smemMax) {
+      int dev = 0, sm = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess) return false;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+      cudaDeviceGetAttribute(&sm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      if (cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm - 1024) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+      }
+      smemMax = sm;
     }
   }
   const size_t cap = (size_t)smemMax - 1024;
@@ -533,15 +540,21 @@ static bool chol_plan(int batch, int n, bool inverse, int* Rout, int* Cout, int*
 static bool chol_cluster_plan(int n, bool inverse, int* Rout, int* Cout) {
   static const bool off = getenv("MPDO_CHOL_NOCLUSTER") != nullptr;   // A/B knob: device-wide barrier through L2
   if (off) return false;
+  static std::mutex initMu;   // see chol_plan: the cached value is published only after the attributes are set
   static int smemMax = 0;
-  if (!smemMax) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return false;
-    cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024) != cudaSuccess ||
-        cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
-      cudaGetLastError();
-      smemMax = -1;
+  {
+    std::lock_guard<std::mutex> lk(initMu);
+    if (!smemMax) {
+      int dev = 0, sm = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess) return false;
+      cudaDeviceGetAttribute(&sm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      if (cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm - 1024) != cudaSuccess ||
+          cudaFuncSetAttribute(chol_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        smemMax = -1;
+      } else {
+        smemMax = sm;
+      }
     }
   }
   if (smemMax <= 0) return false;
@@ -631,7 +644,9 @@ static int chol_launch(int batch, int n, const void* G, void* Y, void* X, void* 
   *rcOut = 0;
   static const bool noSmall = getenv("MPDO_CHOL_NOSMALL") != nullptr;   // A/B knob: always the general kernel
   if (n <= CS_MAXN && batch <= 65535 && !noSmall) {
+    static std::mutex smallMu;
     static bool configured = false;
+    std::unique_lock<std::mutex> smallLock(smallMu);
     if (!configured) {
       if (cudaFuncSetAttribute(chol_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                (int)chol_small_smem(CS_MAXN, true)) != cudaSuccess) {
@@ -640,6 +655,7 @@ static int chol_launch(int batch, int n, const void* G, void* Y, void* X, void* 
       }
       configured = true;
     }
+    smallLock.unlock();
     cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int) * 4 * (size_t)batch, st);
     if (e == cudaSuccess && X) e = cudaMemsetAsync(X, 0, sizeof(double2) * (size_t)batch * n * n, st);
     if (e != cudaSuccess) {

@@ -281,7 +281,10 @@ struct Ctx {
   Ctx(cudaStream_t s, int dtype, int np) : st(s), ar(s), dt(dtype), f32(dtype == MPDO_C64), npass(np) {
     // complex64 states are stored in fp32: rows orthogonal to 1e-10 relative are far below what the state can
     // represent, and Jacobi converges quadratically, so this saves the last sweep or two of every decomposition
-    if (f32) jtol = 1e-10;
+    if (f32) {
+      static const double jt32 = getenv("MPDO_JTOL32") ? atof(getenv("MPDO_JTOL32")) : 1e-10;   // tuning knob
+      jtol = jt32;
+    }
     static const bool noChol = getenv("MPDO_NO_CHOLQR") != nullptr;   // debugging knob
     use_chol = !noChol;
   }

@@ -12,6 +12,8 @@
 // path insensitive to the conditioning of the Gram matrices it feeds in here.
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 
 namespace mpdo {
@@ -648,14 +650,21 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
     if (rc) return rc;
   }
 
+  // one-time set-up behind a mutex (strands call this from several host threads at once; the cached limit must not
+  // be visible before the kernels' shared-memory attributes are set)
+  static std::mutex initMu;
   static int smemMax = 0;
-  if (!smemMax) {
-    int dev = 0;
-    MPDO_CUDA(cudaGetDevice(&dev));
-    MPDO_CUDA(cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024));
-    MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024));
-    MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024));
+  {
+    std::lock_guard<std::mutex> lk(initMu);
+    if (!smemMax) {
+      int dev = 0, sm = 0;
+      MPDO_CUDA(cudaGetDevice(&dev));
+      MPDO_CUDA(cudaDeviceGetAttribute(&sm, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+      MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm - 1024));
+      MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm - 1024));
+      MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm - 1024));
+      smemMax = sm;
+    }
   }
   const long long rowBytes = (long long)mt * sizeof(double2);
   int bmax = (int)((smemMax - 1024) / (2 * rowBytes));
@@ -720,11 +729,13 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
   a.loop = 0;
   // Persistent path: every CTA of the grid must be resident at once (device-wide barrier inside the kernel).
   {
+    static std::mutex coopMu;
     static int coop = -1, sms = 0;
+    std::unique_lock<std::mutex> coopLock(coopMu);
     if (coop < 0) {
-      int dev = 0;
+      int dev = 0, coopAttr = 0;
       MPDO_CUDA(cudaGetDevice(&dev));
-      MPDO_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+      MPDO_CUDA(cudaDeviceGetAttribute(&coopAttr, cudaDevAttrCooperativeLaunch, dev));
       MPDO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
       MPDO_CUDA(cudaFuncSetAttribute(jacobi_persistent_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      smemMax - 1024));
@@ -732,8 +743,9 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
                                      smemMax - 1024));
       MPDO_CUDA(cudaFuncSetAttribute(jacobi_persistent_reg_kernel<16, 512>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smemMax - 1024));
-      if (getenv("MPDO_JACOBI_MULTILAUNCH")) coop = 0;   // debugging knob
+      coop = getenv("MPDO_JACOBI_MULTILAUNCH") ? 0 : coopAttr;   // (debugging knob) published last
     }
+    coopLock.unlock();
     // CTAs per matrix: all nbp/2 block pairs of a round in parallel when the GPU has room, fewer (each CTA then
     // walks several pairs) when the batch is large, down to one CTA per matrix, which needs no device-wide barrier
     // and therefore no cooperative launch (any batch size).
