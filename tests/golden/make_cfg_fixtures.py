@@ -29,6 +29,7 @@ def record(tag, oc, n):
     out[f'{tag}/zz'] = np.array([oc.chain({q: Z, q + 1: Z}).real.item() for q in range(n - 1)])
     out[f'{tag}/p0'] = np.array(oc.chain(proj=[0] * n).real.item())
     out[f'{tag}/rdm_mid'] = oc.rdm([n // 2, n // 2 + 1]).to(torch.complex128).numpy()
+    out[f'{tag}/split_ranks'] = np.array(oc.stats['split_ranks'], dtype=np.int64)   # to tell rank-rule flips apart
 
 
 def cfg1(dtype, mode):

@@ -32,21 +32,32 @@ def gpu_quantities(circ, n):
     }
 
 
-def compare(name, got, dt, tie_floor=False):
-    """complex128: 1e-6 (the reference's absolute rank rule e*1e-8 discards up to 5e-8 of weight per split, and a
-    singular value within rounding of that threshold flips the kept rank - observed 2e-7 on P(0...0) after 12
-    splits; without that rule 1e-10 holds, see test_gpu_parity). complex64: max(1e-5, 3 x the oracle's own complex64-vs-complex128 gap).
+def split_ranks(circ):
+    ranks = circ.last_stats.get('split_ranks', {})
+    return [ranks[k] for k in sorted(ranks)]
+
+
+def compare(name, got, dt, tie_floor=False, ranks=None):
+    """complex128: 1e-10 when the kept rank of every gate split equals the oracle's; a run in which a singular value
+    sits within rounding of the reference's absolute rank-rule threshold (e*1e-8) and the kept rank flips is held to
+    1e-6 instead (the rule then discards up to 5e-8 of weight more or less) and says so. complex64: max(1e-5, 3 x the
+    oracle's own complex64-vs-complex128 gap).
     tie_floor: the circuit has exactly degenerate singular values at its cuts (GHZ symmetry x equally weighted
     depolarizing branches): which 3 of 15 equal branches survive kappa = 4 is decided by rounding noise, the
     reference's own answers spread at the 1e-2 level (precision, SVD branch), and only a 5e-2 sanity bound is
     meaningful; the symmetry-broken variant of the same workload carries the real parity claim."""
     worst = 0.0
+    flips = None
+    if ranks is not None and f'{name}/c128/exact/split_ranks' in FX:
+        want = FX[f'{name}/c128/exact/split_ranks'].tolist()
+        flips = sum(int(a != b) for a, b in zip(ranks, want)) if len(ranks) == len(want) else -1
+        print(f'{name} {dt}: {flips} rank flips in {len(want)} gate splits')
     for key, val in got.items():
         exact = FX[f'{name}/c128/exact/{key}']
         scale = np.abs(exact).max()
         err = np.abs(val - exact).max() / scale
         gap64 = np.abs(FX[f'{name}/c64/exact/{key}'] - exact).max() / scale
-        tol = 1e-6 if dt == 'c128' else max(1e-5, 3 * gap64)
+        tol = (1e-10 if flips == 0 else 1e-6) if dt == 'c128' else max(1e-5, 3 * gap64)
         if tie_floor:
             spread = max(gap64, np.abs(FX[f'{name}/c128/reference/{key}'] - exact).max() / scale)
             tol = max(tol, 3 * spread, 5e-2)
@@ -73,7 +84,7 @@ def run_cfg1(dtype, tiefree):
 @pytest.mark.parametrize('dt', ['c128', 'c64'])
 def test_cfg1_symmetry_broken(cuda_prims, dt):
     c, n = run_cfg1(C128 if dt == 'c128' else C64, tiefree=True)
-    compare('cfg1_tiefree', gpu_quantities(c, n), dt)
+    compare('cfg1_tiefree', gpu_quantities(c, n), dt, ranks=split_ranks(c))
 
 
 @pytest.mark.parametrize('dt', ['c128', 'c64'])
@@ -92,7 +103,7 @@ def test_cfg2_slice(cuda_prims, dt):
     bc.brickwork(c, n, depth, bc.angles([0], bc.n_draws(n, depth, 'rzz')), 'rzz', trunc_after_1q=False)
     st = Simulator.Tools.create_ket0Series(n, dtype=dtype, device='cpu')
     c.evolve(st)
-    compare('cfg2_n6_d3', gpu_quantities(c, n), dt)
+    compare('cfg2_n6_d3', gpu_quantities(c, n), dt, ranks=None if dt == 'c64' else split_ranks(c))
 
 
 def test_batched_sweep_is_deterministic_and_matches_singles(cuda_prims):
@@ -122,10 +133,12 @@ def test_cfg2_full_width_fused_pairs_match_one_split_per_gate(cuda_prims, monkey
     """cfg2 at its full width and truncation parameters (20 qubits, chi 64, kappa 4, czDefault chi-matrix channel on
     every bond), first nine layers (the middle bonds reach chi): the fused CZ pairs of the complex64 path and one split
     per gate (MPDO_NO_FUSE=1), both measured against the complex128 evolution of the same circuit (never fused, fp64
-    throughout) on gauge-invariant outputs. At this size the chi / kappa cuts run through clusters of nearly equal
-    singular values, so fp32-level perturbations are amplified by the truncations; the complex64-vs-complex128 gap
-    of the gate-by-gate path is that floor (same convention as `compare` above), and the fused path must stay within
-    3 x of it."""
+    throughout) on gauge-invariant outputs. This is a sanity check at full width, not the parity claim: there is no
+    oracle at 20 qubits, and at this size the chi / kappa cuts run through clusters of nearly equal singular values,
+    so fp32-level perturbations (including the summation order of the split-K Gram matrices, which differs from run to
+    run) are amplified chaotically - the gate-by-gate path moves between 6e-5 and 6e-4 from run to run. Both paths
+    must stay at that fp32 floor (1.5e-3); the claim against the exact oracle is
+    tests/test_gpu_big_configs.py::test_cfg2_width10_chi64_saturated."""
     n, depth = 20, 9
     files = {'CZ': {f'{i}{i + 1}': bc.chi_file() for i in range(n - 1)}, 'CP': {}}
 
@@ -152,4 +165,4 @@ def test_cfg2_full_width_fused_pairs_match_one_split_per_gate(cuda_prims, monkey
     err_split = np.abs(split - exact).max() / scale
     print(f'bonds {bonds_f}; vs complex128: fused {err_fused:.2e}, one split per gate {err_split:.2e}, '
           f'fused vs split {np.abs(fused - split).max() / scale:.2e}')
-    assert err_fused <= max(2e-5, 3 * err_split)
+    assert err_fused <= 1.5e-3 and err_split <= 1.5e-3
