@@ -21,6 +21,10 @@ from oracle.mpdo_oracle import OracleCircuit  # noqa: E402
 
 Z = torch.tensor([[1, 0], [0, -1]], dtype=torch.complex128)
 out = {}
+# `--only exact_fast` adds that mode to an existing config_fixtures.npz without re-running the slow plain-formulation runs
+ONLY = sys.argv[sys.argv.index('--only') + 1].split(',') if '--only' in sys.argv else None
+if ONLY and os.path.exists(os.path.join(HERE, 'config_fixtures.npz')):
+    out.update(dict(np.load(os.path.join(HERE, 'config_fixtures.npz'))))
 
 
 def record(tag, oc, n):
@@ -32,9 +36,14 @@ def record(tag, oc, n):
     out[f'{tag}/split_ranks'] = np.array(oc.stats['split_ranks'], dtype=np.int64)   # to tell rank-rule flips apart
 
 
+def _kw(mode):
+    """'exact_fast' = exact mode in the oracle's small-side formulation (oracle/mpdo_oracle.py fast=True)."""
+    return dict(svd_mode='exact', fast=True) if mode == 'exact_fast' else dict(svd_mode=mode)
+
+
 def cfg1(dtype, mode):
     n, depth = 10, 10
-    oc = OracleCircuit(n, ideal=False, noiseType='idealNoise', chi=32, kappa=4, chip='medium', dtype=dtype, svd_mode=mode)
+    oc = OracleCircuit(n, ideal=False, noiseType='idealNoise', chi=32, kappa=4, chip='medium', dtype=dtype, **_kw(mode))
     bc.brickwork(oc, n, depth, bc.angles([0], bc.n_draws(n, depth, 'cz')), 'cz', prefix_ghz=True)
     t0 = time.perf_counter()
     oc.evolve()
@@ -46,7 +55,7 @@ def cfg1_tiefree(dtype, mode):
     Kraus branches exactly degenerate at the kappa = 4 cut (the reference's result is then arbitrary at the 1e-2
     level, see cfg1 exact vs reference below); the rotations lift the degeneracy without changing the workload."""
     n, depth = 10, 10
-    oc = OracleCircuit(n, ideal=False, noiseType='idealNoise', chi=32, kappa=4, chip='medium', dtype=dtype, svd_mode=mode)
+    oc = OracleCircuit(n, ideal=False, noiseType='idealNoise', chi=32, kappa=4, chip='medium', dtype=dtype, **_kw(mode))
     pre = bc.angles([7], 3 * n)
     for q in range(n):
         oc.u3(float(pre[3 * q, 0]), float(pre[3 * q + 1, 0]), float(pre[3 * q + 2, 0]), [q], True)
@@ -59,7 +68,7 @@ def cfg1_tiefree(dtype, mode):
 def cfg2_slice(dtype, mode, n=6, depth=3):
     files = {'CZ': {f'{i}{i + 1}': bc.chi_file() for i in range(n - 1)}, 'CP': {}}
     oc = OracleCircuit(n, ideal=False, noiseType='realNoise', chiFileDict=files, chi=64, kappa=4, chip='best',
-                       dtype=dtype, svd_mode=mode)
+                       dtype=dtype, **_kw(mode))
     bc.brickwork(oc, n, depth, bc.angles([0], bc.n_draws(n, depth, 'rzz')), 'rzz', trunc_after_1q=False)
     t0 = time.perf_counter()
     oc.evolve()
@@ -68,8 +77,12 @@ def cfg2_slice(dtype, mode, n=6, depth=3):
 
 for name, fn, n in (('cfg1', cfg1, 10), ('cfg1_tiefree', cfg1_tiefree, 10), ('cfg2_n6_d3', cfg2_slice, 6)):
     for dtype, dt in ((torch.complex128, 'c128'), (torch.complex64, 'c64')):
-        for mode in ('exact', 'reference'):
+        for mode in ('exact', 'exact_fast', 'reference'):
             if name == 'cfg1_tiefree' and mode == 'reference' and dt == 'c64':
+                continue
+            if mode == 'exact_fast' and dt == 'c64':
+                continue
+            if ONLY and mode not in ONLY:
                 continue
             oc, secs = fn(dtype, mode)
             record(f'{name}/{dt}/{mode}', oc, n)

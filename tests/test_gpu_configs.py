@@ -57,7 +57,22 @@ def compare(name, got, dt, tie_floor=False, ranks=None):
         scale = np.abs(exact).max()
         err = np.abs(val - exact).max() / scale
         gap64 = np.abs(FX[f'{name}/c64/exact/{key}'] - exact).max() / scale
-        tol = (1e-10 if flips == 0 else 1e-6) if dt == 'c128' else max(1e-5, 3 * gap64)
+        if dt == 'c128':
+            # Two LAPACK formulations of the reference's own algorithm - the plain one (full two-site matrices) and
+            # the small-side one (oracle fast=True) - agree only to `form_gap` on these circuits (3e-10 ... 2e-7: the
+            # plain formulation decomposes ill-conditioned 72 x 12288-like matrices whose kept singular values span
+            # four decades). The CUDA path is held to 1e-10 against the small-side formulation, whose arithmetic it
+            # shares, and to the formulation gap against the plain one.
+            fast = FX[f'{name}/c128/exact_fast/{key}']
+            form_gap = np.abs(fast - exact).max() / scale
+            err_fast = np.abs(val - fast).max() / np.abs(fast).max()
+            tol = max(1e-10 if flips == 0 else 1e-6, 3 * form_gap)
+            if not tie_floor:
+                print(f'{name} {dt} {key}: vs small-side formulation {err_fast:.2e} (tol '
+                      f'{1e-10 if flips == 0 else 1e-6:.0e}), the two oracle formulations differ by {form_gap:.2e}')
+                assert err_fast <= (1e-10 if flips == 0 else 1e-6), (name, dt, key, err_fast)
+        else:
+            tol = max(1e-5, 3 * gap64)
         if tie_floor:
             spread = max(gap64, np.abs(FX[f'{name}/c128/reference/{key}'] - exact).max() / scale)
             tol = max(tol, 3 * spread, 5e-2)

@@ -471,6 +471,186 @@ static size_t chol_small_smem(int n, bool inverse) {
   return ((inverse ? 2 : 1) * (size_t)n * ld + 2 * (size_t)n) * sizeof(double2);
 }
 
+// ---- medium matrices (CS_MAXN < n <= 256): one 16-CTA thread-block cluster, 16 threads per row ----------------------
+// Same idea as chol_small_kernel with the rows of L dealt to the 16 CTAs of a cluster (<= 16 rows each, transposed
+// slices in shared memory): a dot product is split over 16 lanes (four 64-bit shuffle stages instead of five, two rows
+// per warp in flight), the candidates of a step are exchanged through distributed shared memory behind ONE cluster
+// barrier per pivot step, and the winner's row is gathered straight out of the owning CTA's slice. Column c of the
+// left inverse lives in CTA c % 16 and is extended by a second group of 256 threads while the first computes the new
+// column of L. Outputs, pivot order and stop rule as chol_kernel.
+constexpr int CC_CTAS = 16;        // cluster size (non-portable: > 8)
+constexpr int CC_R = 16;           // rows per CTA, so n <= 256
+constexpr int CC_LD = CC_R + 1;    // odd leading dimension of the transposed slice
+constexpr int CC_THREADS = 512;    // 0..255: 16 rows x 16 lanes;  256..511: 16 inverse columns x 16 lanes
+
+__global__ void __launch_bounds__(CC_THREADS) chol_cluster_kernel(CholArgs p) {
+  extern __shared__ double2 csm[];
+  __shared__ double2 hdr[2];        // own candidate (value, global row) of the even / odd step
+  __shared__ double sVal;
+  __shared__ int sIdx;
+  __shared__ double dl[CC_R];
+  __shared__ int chosen[CC_R];
+  __shared__ int sPiv[CC_CTAS * CC_R];
+  cg::cluster_group cl = cg::this_cluster();
+  const int n = p.n, bidx = blockIdx.y;
+  const int c = (int)cl.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int R = (n + CC_CTAS - 1) / CC_CTAS;
+  const int row0 = c * R;
+  const int rows = max(0, min(R, n - row0));
+  const double2* G = p.G + (long long)bidx * n * n;
+  double2* Y = p.Y + (long long)bidx * n * n;
+  double2* X = p.X ? p.X + (long long)bidx * n * n : nullptr;
+  double2* LT = csm;                               // [n][CC_LD]: LT[j * CC_LD + r] = L[row0 + r, j]
+  double2* prow = LT + (size_t)n * CC_LD;          // [n]: L[pivot, 0..k)
+  double2* grow = prow + n;                        // [CC_R]: G[pivot, own rows]
+  double2* Wc = grow + CC_R;                       // [CC_R][n]: Wc[s * n + j] = W[j, s * 16 + c] (if X)
+  for (int r = tid; r < CC_R; r += CC_THREADS) {
+    dl[r] = r < rows ? G[(long long)(row0 + r) * n + row0 + r].x : -1.0;
+    chosen[r] = r < rows ? 0 : 1;
+  }
+  __syncthreads();
+  double thresh = 0;
+  int rank = n;
+  for (int k = 0; k < n; ++k) {
+    if (tid < 32) {   // own best candidate (ties: lowest row)
+      double v = (lane < CC_R && !chosen[lane]) ? dl[lane] : -1.0;
+      int vi = (lane < CC_R && !chosen[lane]) ? row0 + lane : 0x7fffffff;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+        if (ov > v || (ov == v && oi < vi)) {
+          v = ov;
+          vi = oi;
+        }
+      }
+      if (lane == 0) hdr[k & 1] = make_double2(v, vi == 0x7fffffff ? -1.0 : (double)vi);
+    }
+    cl.sync();        // every CTA's candidate of this step (and its column k-1 of L) is visible cluster-wide
+    if (tid < 32) {
+      double v = -1.0;
+      int vi = 0x7fffffff;
+      if (lane < CC_CTAS) {
+        const double2 h = *cl.map_shared_rank(&hdr[k & 1], lane);
+        if (h.y >= 0) {
+          v = h.x;
+          vi = (int)h.y;
+        }
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+        if (ov > v || (ov == v && oi < vi)) {
+          v = ov;
+          vi = oi;
+        }
+      }
+      if (lane == 0) {
+        sVal = v;
+        sIdx = vi == 0x7fffffff ? -1 : vi;
+      }
+    }
+    __syncthreads();
+    const double pval = sVal;
+    const int pg = sIdx;
+    if (k == 0) thresh = p.rel * pval;
+    if (pg < 0 || !(pval > thresh) || !(pval > 0.0)) {   // the same data in every CTA of the cluster
+      rank = k;
+      break;
+    }
+    {
+      const int owner = pg / R, pr = pg - owner * R;
+      const double2* remote = cl.map_shared_rank(LT, owner);        // columns < k of the winner's row are final
+      for (int j = tid; j < k; j += CC_THREADS) prow[j] = remote[(size_t)j * CC_LD + pr];
+      if (tid >= CC_THREADS - 32 && lane < rows) grow[lane] = G[(long long)pg * n + row0 + lane];
+      if (tid == 0) sPiv[k] = pg;
+    }
+    __syncthreads();
+    const double piv = sqrt(pval), inv = 1.0 / piv;
+    const int t = tid & 15;
+    const unsigned half = (lane < 16) ? 0x0000ffffu : 0xffff0000u;   // the 16 lanes that share a row / a column
+    if (tid < 256) {
+      const int r = tid >> 4;
+      if (r < rows) {                          // uniform over the 16 lanes of a row
+        const int i = row0 + r;
+        const int wasChosen = chosen[r];
+        const double dold = dl[r];
+        double2 out = make_double2(0.0, 0.0);
+        double dnew = dold;
+        double ar = 0, ai = 0;
+        if (i != pg && !wasChosen)
+          for (int j = t; j < k; j += 16) {   // sum_j L[i,j] conj(L[p,j])
+            const double2 a = LT[(size_t)j * CC_LD + r], b = prow[j];
+            ar = fma(a.x, b.x, fma(a.y, b.y, ar));
+            ai = fma(a.y, b.x, fma(-a.x, b.y, ai));
+          }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          ar += __shfl_xor_sync(half, ar, o);
+          ai += __shfl_xor_sync(half, ai, o);
+        }
+        if (i == pg) {
+          out.x = piv;
+        } else if (!wasChosen) {
+          const double2 g = grow[r];           // G[p,i]; G[i,p] is its conjugate
+          out.x = (g.x - ar) * inv;
+          out.y = (-g.y - ai) * inv;
+          dnew = fmax(dold - (out.x * out.x + out.y * out.y), 0.0);
+        }
+        __syncwarp(half);                      // dl / chosen were read by all 16 lanes before the leader updates them
+        if (t == 0) {
+          if (i == pg)
+            chosen[r] = 1;
+          else if (!wasChosen)
+            dl[r] = dnew;
+          LT[(size_t)k * CC_LD + r] = out;
+          Y[(long long)k * n + i] = make_double2(out.x, -out.y);
+        }
+      }
+    } else {
+      // row k of W = L11^-1 (pivot order); column col = s * 16 + c is extended by slot s of this CTA:
+      //   W[k,k] = 1/piv,  W[k,col] = -(sum_{col<=j<k} L[p_k,j] W[j,col]) / piv
+      const int s_ = (tid - 256) >> 4;
+      const int col = s_ * CC_CTAS + c;
+      const bool active = X != nullptr && col <= k && col < n;   // uniform over the 16 lanes of a slot
+      if (active) {
+        double ar = 0, ai = 0;
+        if (col < k) {
+          const double2* wcol = Wc + (size_t)s_ * n;
+          for (int j = col + t; j < k; j += 16) {
+            const double2 a = prow[j], b = wcol[j];
+            ar = fma(a.x, b.x, fma(-a.y, b.y, ar));
+            ai = fma(a.x, b.y, fma(a.y, b.x, ai));
+          }
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+          ar += __shfl_xor_sync(half, ar, o);
+          ai += __shfl_xor_sync(half, ai, o);
+        }
+        if (t == 0) {
+          const double2 w = col == k ? make_double2(inv, 0.0) : make_double2(-ar * inv, -ai * inv);
+          Wc[(size_t)s_ * n + k] = w;
+          X[(long long)k * n + (col == k ? pg : sPiv[col])] = w;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  cl.sync();   // nobody leaves while a neighbour may still read its slice
+  for (long long idx = tid; idx < (long long)(n - rank) * rows; idx += CC_THREADS) {
+    const int k = rank + (int)(idx / rows), r = (int)(idx % rows);
+    Y[(long long)k * n + row0 + r] = make_double2(0.0, 0.0);       // rows of Y beyond the rank are zero
+  }
+  if (c == 0 && tid == 0) p.info[4LL * bidx] = rank;
+}
+
+static size_t chol_cluster_smem(int n, bool inverse) {
+  return ((size_t)n * CC_LD + (size_t)n + CC_R + (inverse ? (size_t)CC_R * n : 0)) * sizeof(double2);
+}
+
 static size_t chol_smem(int n, int R, bool inverse) {
   return chol_ws_offset(n, R) + (inverse ? (size_t)R * n * sizeof(double2) : 0);
 }
@@ -678,6 +858,77 @@ static int chol_launch(int batch, int n, const void* G, void* Y, void* X, void* 
     chol_small_kernel<<<dim3(1, batch), CS_THREADS, chol_small_smem(n, X != nullptr), st>>>(a);
     *rcOut = check_launch("chol_small_kernel");
     return 0;
+  }
+  static const bool noCluster16 = getenv("MPDO_CHOL_NOCLUSTER16") != nullptr;   // A/B knob
+  if (n > CS_MAXN && n <= CC_CTAS * CC_R && batch <= 65535 && !noCluster16) {
+    static std::mutex ccMu;
+    static int ccOk = -1;    // 1: usable (attributes set, a cluster of 16 fits), 0: not
+    {
+      std::lock_guard<std::mutex> lk(ccMu);
+      if (ccOk < 0) {
+        ccOk = 0;
+        if (cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)chol_cluster_smem(CC_CTAS * CC_R, true)) == cudaSuccess &&
+            cudaFuncSetAttribute(chol_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+          cudaLaunchConfig_t q = {};
+          q.gridDim = dim3(CC_CTAS, 1);
+          q.blockDim = dim3(CC_THREADS);
+          q.dynamicSmemBytes = chol_cluster_smem(CC_CTAS * CC_R, true);
+          cudaLaunchAttribute qa[1];
+          qa[0].id = cudaLaunchAttributeClusterDimension;
+          qa[0].val.clusterDim.x = CC_CTAS;
+          qa[0].val.clusterDim.y = 1;
+          qa[0].val.clusterDim.z = 1;
+          q.attrs = qa;
+          q.numAttrs = 1;
+          int nClusters = 0;
+          if (cudaOccupancyMaxActiveClusters(&nClusters, chol_cluster_kernel, &q) == cudaSuccess && nClusters >= 1)
+            ccOk = 1;
+        }
+        if (!ccOk) cudaGetLastError();
+      }
+    }
+    if (ccOk == 1) {
+      cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int) * 4 * (size_t)batch, st);
+      if (e == cudaSuccess && X) e = cudaMemsetAsync(X, 0, sizeof(double2) * (size_t)batch * n * n, st);
+      if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "chol memset: %s", cudaGetErrorString(e));
+        *rcOut = (int)e;
+        return 0;
+      }
+      CholArgs a;
+      a.n = n;
+      a.R = (n + CC_CTAS - 1) / CC_CTAS;
+      a.rel = rel;
+      a.G = (const double2*)G;
+      a.Y = (double2*)Y;
+      a.X = (double2*)X;
+      a.slots = nullptr;
+      a.info = info;
+      a.cluster = 1;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(CC_CTAS, batch);
+      cfg.blockDim = dim3(CC_THREADS);
+      cfg.dynamicSmemBytes = chol_cluster_smem(n, X != nullptr);
+      cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = CC_CTAS;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      const double cflops = 8.0 * batch * ((double)n * n * n / 3.0) * (X ? 2.0 : 1.0);
+      TimedLaunch timed(2, cflops, 16.0 * batch * (double)n * n * (X ? 3.0 : 2.0), st);
+      e = cudaLaunchKernelEx(&cfg, chol_cluster_kernel, a);
+      if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "chol_cluster_kernel: %s", cudaGetErrorString(e));
+        *rcOut = (int)e;
+        return 0;
+      }
+      *rcOut = check_launch("chol_cluster_kernel");
+      return 0;
+    }
   }
   bool cluster = false;
   int optin = 0, dev = 0;
