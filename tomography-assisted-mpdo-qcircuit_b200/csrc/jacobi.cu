@@ -14,7 +14,11 @@
 
 #include <mutex>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace mpdo {
 
@@ -444,6 +448,253 @@ __global__ void __launch_bounds__(MAXT) jacobi_persistent_reg_kernel(JacobiArgs 
   }
 }
 
+// ---- cluster-resident tournament (2b < n <= 32 b): the matrix never leaves the SMs ----------------------------------
+// One thread-block cluster of nbp/2 <= 16 CTAs per matrix; CTA q keeps the two row blocks of tournament pair q in its
+// shared memory for the whole decomposition. Between rounds the blocks travel to their next CTA through distributed
+// shared memory (each warp pulls one row of each block into registers, cluster barrier, then stores it locally), so
+// there is no L2 round trip and no device-wide barrier, and any batch size can be launched (clusters are scheduled
+// independently: nothing has to be co-resident beyond one cluster).
+// The cross-pair steps are register-resident: warp q holds row q of block I in registers for the whole round and
+// meets the rows of block J one after the other; a row of J is loaded from shared memory ONCE per step, rotated in
+// registers and stored once (2 row passes per rotation instead of the 6 of rotate_pair). ncu on the persistent kernel
+// showed the steps bound by shared-memory bandwidth (196 KB per step and SM, 1.5 k of ~2.5 k cycles) and 30% of the
+// time in L2 staging and the device-wide barrier; both go away here.
+
+// Sum four doubles over the warp with 10 double shuffles instead of 20: the first two levels halve the number of
+// values a lane carries while halving the lanes that carry each, the last three are plain butterflies, then the four
+// totals are broadcast from their lane classes.
+__device__ __forceinline__ void warp_sum4(double& v0, double& v1, double& v2, double& v3, int lane) {
+  const bool h4 = (lane & 16) != 0;
+  double s0 = h4 ? v0 : v2, s1 = h4 ? v1 : v3;
+  double k0 = h4 ? v2 : v0, k1 = h4 ? v3 : v1;
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  const bool h3 = (lane & 8) != 0;
+  const double s = h3 ? k0 : k1;
+  double k = h3 ? k1 : k0;
+  k += __shfl_xor_sync(0xffffffffu, s, 8);
+  k += __shfl_xor_sync(0xffffffffu, k, 4);
+  k += __shfl_xor_sync(0xffffffffu, k, 2);
+  k += __shfl_xor_sync(0xffffffffu, k, 1);
+  v0 = __shfl_sync(0xffffffffu, k, 0);
+  v1 = __shfl_sync(0xffffffffu, k, 8);
+  v2 = __shfl_sync(0xffffffffu, k, 16);
+  v3 = __shfl_sync(0xffffffffu, k, 24);
+}
+
+// Rotation of the register-resident row x (entry k = lane + 32 e) against row y of shared memory: y is loaded once,
+// rotated in registers and stored once. `active` is warp-uniform. Entries of x beyond mt are zero and stay zero.
+template <int E>
+__device__ __forceinline__ int rotate_regs(double2 (&x)[E], double2* __restrict__ yrow, bool active, int m, int mt,
+                                           double tol, double floor2, int lane) {
+  if (!active) return 0;
+  double2 y[E];
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int k = lane + 32 * e;
+    y[e] = k < mt ? yrow[k] : make_double2(0.0, 0.0);
+  }
+  double a = 0, bq = 0, gr = 0, gi = 0;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    if (lane + 32 * e < m) {
+      const double2 u = x[e], v = y[e];
+      a = fma(u.x, u.x, fma(u.y, u.y, a));
+      bq = fma(v.x, v.x, fma(v.y, v.y, bq));
+      gr = fma(u.x, v.x, fma(u.y, v.y, gr));
+      gi = fma(u.y, v.x, fma(-u.x, v.y, gi));
+    }
+  }
+  warp_sum4(a, bq, gr, gi, lane);
+  const double g2 = gr * gr + gi * gi;
+  const double ab = a * bq;
+  if (!(ab > floor2) || !(g2 > tol * tol * ab)) return 0;
+  const double d = 0.5 * (bq - a);
+  const double ad = fabs(d);
+  const double qq = fma(d, d, g2);
+  const double h = qq * rsqrt(qq);   // g2 > 0 here; a couple of ulps off the rounded root is immaterial for the angle
+  const double ru = rsqrt(2.0 * h * (h + ad));
+  const double c = (h + ad) * ru;
+  const double sg = d >= 0 ? ru : -ru;
+  const double sr = sg * gr, si = sg * gi;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const int k = lane + 32 * e;
+    const double2 u = x[e], v = y[e];
+    double2 xn, yn;
+    xn.x = fma(c, u.x, fma(-sr, v.x, si * v.y));
+    xn.y = fma(c, u.y, -fma(sr, v.y, si * v.x));
+    yn.x = fma(c, v.x, fma(sr, u.x, si * u.y));
+    yn.y = fma(c, v.y, fma(sr, u.y, -si * u.x));
+    x[e] = xn;
+    if (k < mt) yrow[k] = yn;
+  }
+  return 1;
+}
+
+constexpr int JC_MAXC = 16;   // CTAs per cluster (non-portable above 8)
+
+// Schedule: odd-even transposition over the nbp block positions (CTA q owns positions 2q and 2q+1, buffers A and B).
+// Even rounds pair the two local blocks and swap their positions (a pointer swap); odd rounds pair position 2q-1 -
+// CTA q pulls the B block of its left neighbour straight into registers - with the local A block, after which the
+// pulled block stays (new A) and the old A rows are pushed into the neighbour's B buffer. Every pair of blocks meets
+// exactly once in nbp rounds from any starting arrangement, and only ONE block per CTA crosses the cluster per two
+// rounds in each direction (the round-robin tournament moves both blocks of every CTA every round; distributed shared
+// memory moves ~20 B per clock and SM, which made that exchange a quarter of the run time), behind one cluster
+// barrier per round.
+template <int E>
+__global__ void __launch_bounds__(256, 1) jacobi_cluster_kernel(JacobiArgs p, double2* __restrict__ Yall) {
+  extern __shared__ double2 smem[];   // [2 buffers][b rows][mt]
+  __shared__ int flags[JC_MAXC];      // per-CTA "rotated in this sweep", written by every CTA of the cluster
+  __shared__ int perm[2 * JC_MAXC];   // block index at every position (the same simulation in every CTA)
+  cg::cluster_group cl = cg::this_cluster();
+  const int q = (int)blockIdx.x;      // cluster = the gridDim.x CTAs of one matrix: rank in cluster == blockIdx.x
+  const int C = (int)gridDim.x;
+  const int bidx = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;   // b warps
+  const int b = p.b, mt = p.mt;
+  int* cnt = p.cnt + (long long)bidx * WORK_INTS;
+  const double amax = *reinterpret_cast<const double*>(cnt + 32);
+  const double floor2 = fmax(1e-290, 1e-48 * amax * amax);
+  double2* Y = Yall + (long long)bidx * p.batchStride;
+  const int nrows = p.rank ? min(p.n, p.rank[(long long)bidx * p.rankStride]) : p.n;
+  if (nrows < 2) return;              // uniform over the cluster: nobody reaches a barrier
+  const int nbp = (((nrows + b - 1) / b) + 1) & ~1;   // blocks that hold non-zero rows, rounded up to even
+  const int Ca = nbp / 2;             // CTAs that take part (<= C by construction of the launch)
+  const bool act = q < Ca;
+  const int be = (b + 1) & ~1, half = be / 2;
+  double2* bufA = smem;
+  double2* bufB = smem + (size_t)b * mt;
+  if (threadIdx.x < JC_MAXC) flags[threadIdx.x] = 0;
+  if (threadIdx.x < 2 * JC_MAXC) perm[threadIdx.x] = threadIdx.x;
+  if (act) {
+    for (int v = warp; v < 2 * b; v += b) {
+      const int row = 2 * q * b + v;   // block 2q -> A, block 2q+1 -> B
+      double2* dst = smem + (size_t)v * mt;
+      if (row < nrows) {
+        const double2* src = Y + (long long)row * p.ld;
+        for (int k = lane; k < mt; k += 32) dst[k] = src[k];
+      } else {
+        for (int k = lane; k < mt; k += 32) dst[k] = make_double2(0.0, 0.0);
+      }
+    }
+  }
+  __syncthreads();
+
+  double2 x[E];
+  for (int sw = 0; sw < p.maxSweeps; ++sw) {
+    int rot = 0;
+    for (int round = 0; round < nbp; ++round) {
+      if ((round & 1) == 0) {
+        // ---- even round: the two local blocks ------------------------------------------------------------------
+        if (act) {
+          const int idA = perm[2 * q], idB = perm[2 * q + 1];
+          if (round == 0) {   // once per sweep: the pairs inside each of the two blocks, both rows in shared memory
+            for (int step = 0; step < be - 1; ++step) {
+              for (int base = 0; base < be; base += b) {
+                const int qq = base + warp;
+                const int blk = qq >= half ? 1 : 0;
+                int a0, a1;
+                rr_pair(be, step, qq - blk * half, a0, a1);
+                const int firstRow = (blk ? idB : idA) * b;
+                double2* rows = blk ? bufB : bufA;
+                const bool on = qq < be && a0 < b && a1 < b && firstRow + a0 < nrows && firstRow + a1 < nrows;
+                rot |= rotate_pair<32>(rows + (size_t)a0 * mt, rows + (size_t)a1 * mt, on, p.m, mt, p.tol, floor2, lane);
+              }
+              __syncthreads();
+            }
+          }
+          double2* xs = bufA + (size_t)warp * mt;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int k = lane + 32 * e;
+            x[e] = k < mt ? xs[k] : make_double2(0.0, 0.0);
+          }
+          const bool mine = idA * b + warp < nrows;
+          for (int step = 0; step < b; ++step) {
+            int a1 = warp + step;
+            if (a1 >= b) a1 -= b;
+            const bool on = mine && idB * b + a1 < nrows;
+            rot |= rotate_regs<E>(x, bufB + (size_t)a1 * mt, on, p.m, mt, p.tol, floor2, lane);
+            __syncthreads();
+          }
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int k = lane + 32 * e;
+            if (k < mt) xs[k] = x[e];
+          }
+        }
+        {   // the two positions of every CTA swap (same pointer parity in every CTA of the cluster)
+          double2* t = bufA;
+          bufA = bufB;
+          bufB = t;
+        }
+        __syncthreads();   // perm was read above
+        if (threadIdx.x < Ca) {
+          const int t = perm[2 * threadIdx.x];
+          perm[2 * threadIdx.x] = perm[2 * threadIdx.x + 1];
+          perm[2 * threadIdx.x + 1] = t;
+        }
+      } else {
+        // ---- odd round: position 2q-1 (B of the left neighbour) against position 2q (local A) --------------------
+        if (act && q >= 1) {
+          const int idX = perm[2 * q - 1], idY = perm[2 * q];
+          double2* remoteB = cl.map_shared_rank(bufB, q - 1) + (size_t)warp * mt;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int k = lane + 32 * e;
+            x[e] = k < mt ? remoteB[k] : make_double2(0.0, 0.0);
+          }
+          const bool mine = idX * b + warp < nrows;
+          for (int step = 0; step < b; ++step) {
+            int a1 = warp + step;
+            if (a1 >= b) a1 -= b;
+            const bool on = mine && idY * b + a1 < nrows;
+            rot |= rotate_regs<E>(x, bufA + (size_t)a1 * mt, on, p.m, mt, p.tol, floor2, lane);
+            __syncthreads();
+          }
+          // the rotated local block moves to position 2q-1 (the neighbour's B), the pulled block stays as the new A
+          double2* ys = bufA + (size_t)warp * mt;
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int k = lane + 32 * e;
+            if (k < mt) {
+              remoteB[k] = ys[k];
+              ys[k] = x[e];
+            }
+          }
+        }
+        __syncthreads();   // perm was read above
+        if (threadIdx.x + 1 < Ca) {
+          const int t = perm[2 * threadIdx.x + 1];
+          perm[2 * threadIdx.x + 1] = perm[2 * threadIdx.x + 2];
+          perm[2 * threadIdx.x + 2] = t;
+        }
+      }
+      if (round == nbp - 1) {   // end of the sweep: tell every CTA of the cluster whether this one rotated
+        const int any = __syncthreads_or(rot);
+        if (threadIdx.x < C) cl.map_shared_rank(flags, threadIdx.x)[q] = any;
+      }
+      cl.sync();   // parked / pushed rows (and the sweep flags) are visible cluster-wide; perm is updated
+    }
+    int anyAll = 0;
+    for (int c = 0; c < C; ++c) anyAll |= flags[c];
+    if (q == 0 && threadIdx.x == 0) cnt[sw] = anyAll;
+    if (!anyAll) break;   // the same flags in every CTA
+  }
+
+  if (act) {
+    for (int v = warp; v < 2 * b; v += b) {
+      const int row = perm[2 * q + (v < b ? 0 : 1)] * b + (v < b ? v : v - b);
+      if (row < nrows) {
+        double2* dst = Y + (long long)row * p.ld;
+        const double2* src = (v < b ? bufA : bufB) + (size_t)(v < b ? v : v - b) * mt;
+        for (int k = lane; k < mt; k += 32) dst[k] = src[k];
+      }
+    }
+  }
+}
+
 // max over rows of |row[0..m)|^2, stored as a double after the 32 sweep counters of each batch entry
 __global__ void __launch_bounds__(256) row_norm_max_kernel(int n, int m, int ld, long long batchStride,
                                                            const double2* __restrict__ Yall, int* __restrict__ work) {
@@ -629,6 +880,68 @@ __global__ void __launch_bounds__(256) rows_setup_kernel(int n, int m, const dou
   }
 }
 
+
+// Launch of the cluster-resident tournament. Returns -1 when the shape / device cannot run it (the caller takes the
+// older paths), 0 on success, a CUDA error code otherwise.
+static int jacobi_cluster_launch(const JacobiArgs& a0, int batch, double2* Y, cudaStream_t st) {
+  constexpr int bc = 8;
+  const int n = a0.n, mt = a0.mt;
+  const int C = (((n + bc - 1) / bc) + 1) / 2;
+  if (C < 2 || C > JC_MAXC || mt > 512) return -1;
+  // one cluster per matrix, one CTA per SM (registers): batches beyond a single wave of clusters keep the older
+  // kernels, whose throughput per matrix is better once the GPU is full (measured: 128 x n = 128 9.7 vs 12.9 ms)
+  static const int maxCtas = getenv("MPDO_JACOBI_CLUSTER_CTAS") ? atoi(getenv("MPDO_JACOBI_CLUSTER_CTAS")) : 148;
+  if ((long long)batch * C > maxCtas) return -1;
+  const int E = mt <= 64 ? 2 : (mt <= 128 ? 4 : (mt <= 256 ? 8 : 16));
+  const void* fn = E == 2 ? (const void*)jacobi_cluster_kernel<2>
+                 : E == 4 ? (const void*)jacobi_cluster_kernel<4>
+                 : E == 8 ? (const void*)jacobi_cluster_kernel<8> : (const void*)jacobi_cluster_kernel<16>;
+  const size_t smem = (size_t)2 * bc * mt * sizeof(double2);
+  static std::mutex mu;
+  static int ok[5][JC_MAXC + 1];   // per (E class, cluster size): 0 unknown, 1 usable, -1 not
+  const int ei = E == 2 ? 0 : (E == 4 ? 1 : (E == 8 ? 2 : 3));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C, batch);
+  cfg.blockDim = dim3(32 * bc);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (ok[ei][C] == 0) {
+      ok[ei][C] = -1;
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * bc * 32 * E * (int)sizeof(double2)) ==
+              cudaSuccess &&
+          cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+        cudaLaunchConfig_t qc = cfg;
+        qc.gridDim = dim3(C, 1);
+        qc.dynamicSmemBytes = (size_t)2 * bc * 32 * E * sizeof(double2);
+        int nClusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&nClusters, fn, &qc) == cudaSuccess && nClusters >= 1) ok[ei][C] = 1;
+      }
+      if (ok[ei][C] < 0) cudaGetLastError();
+    }
+    if (ok[ei][C] < 0) return -1;
+  }
+  JacobiArgs a = a0;
+  a.b = bc;
+  a.nbp = 2 * C;
+  a.loop = 0;
+  void* args[] = {(void*)&a, (void*)&Y};
+  TimedLaunch timed(1, 4.0 * batch * (6.0 * a.m * (double)n * n + 20.0 * (double)n * n * n), 32.0 * batch * (double)n * a.m, st);
+  cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "jacobi_cluster_kernel (cluster of %d): %s", C, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return check_launch("jacobi_cluster_kernel");
+}
 }  // namespace mpdo
 
 namespace mpdo {
@@ -664,6 +977,29 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
       MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm - 1024));
       MPDO_CUDA(cudaFuncSetAttribute(jacobi_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm - 1024));
       smemMax = sm;
+    }
+  }
+  {
+    // cluster-resident tournament for everything between "fits one CTA comfortably" and 256 rows (see
+    // jacobi_cluster_kernel); MPDO_JACOBI_NOCLUSTER / MPDO_JACOBI_CLUSTER_MIN are A/B knobs
+    static const bool noCluster = getenv("MPDO_JACOBI_NOCLUSTER") != nullptr;
+    static const int clusterMin = getenv("MPDO_JACOBI_CLUSTER_MIN") ? atoi(getenv("MPDO_JACOBI_CLUSTER_MIN")) : 33;
+    if (!noCluster && n >= clusterMin && n > 16 && n <= 16 * JC_MAXC && mt <= 512) {
+      JacobiArgs a;
+      a.n = n;
+      a.m = m;
+      a.mt = mt;
+      a.ld = ld;
+      a.batchStride = batchStride;
+      a.round = 0;
+      a.sweep = 0;
+      a.maxSweeps = maxSweeps;
+      a.tol = tol;
+      a.cnt = work;
+      a.rank = rank;
+      a.rankStride = rankStride;
+      const int rc = jacobi_cluster_launch(a, batch, (double2*)Y, st);
+      if (rc >= 0) return rc;
     }
   }
   const long long rowBytes = (long long)mt * sizeof(double2);
