@@ -262,3 +262,55 @@ def test_cz_pair_fusion_with_batched_angles():
         prog(single, [float(theta[q, b]) for q in range(n - 1)])
         single.evolve(Simulator.Tools.create_ket0Series(n, dtype=C64))
         assert rel(rho_b[b], single.cal_dm()) < 2e-5
+
+
+def test_segment_compilation_is_reused_and_follows_the_gates(monkeypatch):
+    """truncate() compiles the segment it closes (strands, fused Kraus composites); evolve() reuses the compiled
+    segment while the gates are unchanged and recompiles when a gate parameter is modified in place."""
+    n = 4
+    files = {'CZ': {f'{i}{i + 1}': os.path.join(CHI_DIR, 'czDefault.mat') for i in range(n - 1)}, 'CP': {}}
+
+    def build():
+        c = Simulator.TensorCircuit(qn=n, ideal=False, noiseType='realNoise', chiFileDict=files, chi=8, kappa=4,
+                                    chip='best', dtype=C128, device='cpu')
+        for q in range(n):
+            c.u3(0.3 + q, 0.2, 0.1, [q])
+        c.rzz(0.7, 0, 1)
+        c.rzz(0.4, 2, 3)
+        c.truncate()
+        c.rzz(0.9, 1, 2)
+        c.truncate()
+        return c
+
+    calls = []
+    orig = Simulator.TensorCircuit._compile_segment
+
+    def counting(self, ops):
+        calls.append(len(ops))
+        return orig(self, ops)
+
+    monkeypatch.setattr(Simulator.TensorCircuit, '_compile_segment', counting)
+    c = build()
+    assert len(calls) == 2 and len(c._compiled) == 2           # compiled at construction
+    s1 = Simulator.Tools.create_ket0Series(n, dtype=C128, device='cpu')
+    c.evolve(s1)
+    assert len(calls) == 2                                      # nothing rebuilt inside evolve
+    z1 = c.cal_dm().clone()
+    s2 = Simulator.Tools.create_ket0Series(n, dtype=C128, device='cpu')
+    c.evolve(s2)
+    assert len(calls) == 2 and torch.equal(c.cal_dm(), z1)      # a second evolve is the same computation
+
+    monkeypatch.setenv('MPDO_LAZY_COMPILE', '1')
+    lazy = build()
+    assert len(calls) == 2 and not lazy._compiled
+    s3 = Simulator.Tools.create_ket0Series(n, dtype=C128, device='cpu')
+    lazy.evolve(s3)
+    assert len(calls) == 4 and torch.equal(lazy.cal_dm(), z1)   # compiled on first use, same numbers
+    monkeypatch.delenv('MPDO_LAZY_COMPILE')
+
+    gate = next(g for g in c.layers if getattr(g, 'name', '') == 'U3')
+    gate.theta.add_(0.5)                                        # in-place change of a gate parameter
+    s4 = Simulator.Tools.create_ket0Series(n, dtype=C128, device='cpu')
+    c.evolve(s4)
+    assert len(calls) == 5                                      # only the segment holding that gate
+    assert not torch.allclose(c.cal_dm(), z1)

@@ -54,6 +54,8 @@ class TensorCircuit(QuantumCircuit):
             if self.realNoise:
                 self._load_exp_tensors()
         self.last_stats = {}
+        self._compiled = {}      # segment (tuple of layer indices) -> (stamp, programs, noisy 2q count)
+        self._segment_start = 0
 
     # ------------------------------------------------------------------------------------------------
     # gate operands (host) -> device
@@ -318,14 +320,28 @@ class TensorCircuit(QuantumCircuit):
             svdKappa_left2right(state, max_singular_values=self.kappa, max_truncation_err=self.max_truncation_err)
         self._stateNodes = state
 
-    def _run_segment(self, state: List[DenseNode], segment: list):
-        """Apply the gates collected since the last truncate. Gates are grouped into strands of qubits that do
-        not interact inside the segment (order inside a strand is the circuit order); strands are independent,
-        so they are issued concurrently (one CUDA stream each, _engine/strands.py)."""
-        if not segment:
-            return
-        ops = [(i, g, oqs) for i, g, oqs in segment if oqs and oqs[0] is not None]
-        segment.clear()
+    # ------------------------------------------------------------------------------------------------
+    # segment compilation (host): strands, primitive steps, fused Kraus composites, device operands
+    # ------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _stamp(ops):
+        """Identity + in-place version of every tensor a gate of the segment holds: a compiled segment is reused
+        only while its gates are the ones it was compiled from."""
+        out = []
+        for _, g, oqs in ops:
+            out.append((id(g), tuple(oqs)))
+            for v in vars(g).values():
+                if isinstance(v, tc.Tensor):
+                    out.append((id(v), v._version))
+        return tuple(out)
+
+    def _compile_segment(self, ops: list):
+        """Host side of one segment (the gates between two truncate markers): split the gates into strands of qubits
+        that do not interact inside the segment, resolve every strand into primitive steps on gate operands
+        (_program: Kraus composites of fused pairs, minimal Kraus representation, SWAP routing) and place the
+        operands on the circuit's device. Pure operand building, as the reference's gate constructors and its
+        noiseTensorDict cache do - done once per segment when `truncate()` closes it (or on first use) and reused by
+        every evolve() while the gates are unchanged. Returns (stamp, programs, noisy two-qubit gate count)."""
         for _, _, oqs in ops:
             if not isinstance(oqs, List):
                 raise TypeError('Operating qubits must be a list.')
@@ -345,9 +361,59 @@ class TensorCircuit(QuantumCircuit):
         strands = {}
         for op in ops:
             strands.setdefault(find(op[2][0]), []).append(op)
-        for _, g, _ in ops:
-            if isinstance(g, QuantumGate) and not g.single and ((self.idealNoise and not g.ideal) or self.realNoise):
-                self.last_stats['noisy_2q_updates'] = self.last_stats.get('noisy_2q_updates', 0) + 1
+        noisy2q = sum(1 for _, g, _ in ops if isinstance(g, QuantumGate) and not g.single
+                      and ((self.idealNoise and not g.ideal) or self.realNoise))
+        programs = [self._program(chain) for chain in strands.values()]
+        if tc.device(self.device).type == 'cuda' and tc.cuda.is_available():
+            uploaded = {}
+
+            def up(G):
+                if id(G) not in uploaded:
+                    uploaded[id(G)] = self._dev(G)
+                return uploaded[id(G)]
+
+            programs = [(qubits, [st[:2] + (up(st[2]),) + st[3:] if st[0] == '1q' else st[:3] + (up(st[3]),) + st[4:]
+                                  for st in steps]) for qubits, steps in programs]
+        return self._stamp(ops), programs, noisy2q
+
+    def _segment_ops(self, first: int, last: int):
+        import itertools
+        mods = itertools.islice(self.layers._modules.values(), first, last)   # nn.Sequential indexing is O(n)
+        return [(i, g, self._oqs_list[i]) for i, g in zip(range(first, last), mods)
+                if self._oqs_list[i] and self._oqs_list[i][0] is not None
+                and 'barrier' not in getattr(g, 'name', '').lower()]
+
+    def truncate(self):
+        """Add a truncation layer; the segment it closes is compiled here (host operand building belongs to circuit
+        construction, as in the reference, not to evolve). Construction never raises for it: a segment that cannot be
+        compiled raises from evolve(), where the reference raises."""
+        first = getattr(self, '_segment_start', 0)
+        super().truncate()
+        last = len(self._oqs_list) - 1
+        self._segment_start = last + 1
+        if os.environ.get('MPDO_LAZY_COMPILE'):
+            return
+        try:
+            ops = self._segment_ops(first, last)
+            if ops:
+                self._compiled[tuple(i for i, _, _ in ops)] = self._compile_segment(ops)
+        except Exception:   # noqa: BLE001  (evolve() compiles again and raises there)
+            pass
+
+    def _run_segment(self, state: List[DenseNode], segment: list):
+        """Apply the gates collected since the last truncate. Gates are grouped into strands of qubits that do
+        not interact inside the segment (order inside a strand is the circuit order); strands are independent,
+        so they are issued concurrently (one CUDA stream each, _engine/strands.py)."""
+        if not segment:
+            return
+        ops = [(i, g, oqs) for i, g, oqs in segment if oqs and oqs[0] is not None]
+        segment.clear()
+        key = tuple(i for i, _, _ in ops)
+        entry = self._compiled.get(key)
+        if entry is None or entry[0] != self._stamp(ops):
+            entry = self._compiled[key] = self._compile_segment(ops)
+        _, programs, noisy2q = entry
+        self.last_stats['noisy_2q_updates'] = self.last_stats.get('noisy_2q_updates', 0) + noisy2q
 
         # Strands are issued concurrently, one CUDA stream each. With MPDO_GROUPING=1 strands whose step sequences
         # and tensor shapes coincide (the bulk brick pairs of a layer) are instead stacked along the batch axis and run
@@ -356,7 +422,6 @@ class TensorCircuit(QuantumCircuit):
         # contractions of one pair behind the factorisations of another, and a batch-wide stall of the top-kappa
         # iteration sends every member down the full decomposition) - so it is opt-in.
         cuda = getattr(_engine.get_prims(), 'name', '') == 'cuda'
-        programs = [self._program(chain) for chain in strands.values()]
         groups = {}
         for prog in programs:
             key = self._signature(state, prog) if os.environ.get('MPDO_GROUPING', '0') == '1' else id(prog)
