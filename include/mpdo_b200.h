@@ -165,6 +165,29 @@ int mpdo_qr_step(int dtype, int npass, int B, int l, int a, int r, const void* T
 int mpdo_bond_svd_step(int dtype, int npass, int B, int lp, int ap, int l, const void* Tl, int a, int r, const void* Tr,
                        int k, double max_err, int* k_out, void* Tl_out, void* Tr_out, double* sv_out, void* stream);
 
+/* bondTruncate (QR sweep + chi sweep) in environment form, for complex64 states and a fixed chi: same singular values
+ * and the same sqrt(S) | sqrt(S) split at every bond as mpdo_qr_step + mpdo_bond_svd_step, but only ONE sequential
+ * chain of decompositions.
+ * mpdo_env_sweep: sites T[i] [B, l[i], 2, a[i], r[i]] (l[0] = 1, l[i+1] = r[i]), i = 0 .. nsites-1. For every bond
+ * j = 1 .. nsites-1 it forms the left environment E_j = A_j^h A_j (A_j = the block of sites 0 .. j-1; the chain
+ * E_{i+1} = T_i^h E_i T_i is two contractions per site and is the Gram matrix the QR sweep would factor), factors it
+ * rank-revealingly, E_j = C^h C, and writes the left inverse (Ci . C^h = 1 on the numerical range) to Ci_out[j]
+ * ([B, l[j], l[j]] complex128) and the product C . T[j] to M_out[j] ([B, l[j], 2, a[j], r[j]], state dtype); entries 0
+ * of the pointer arrays are unused. The factorisations and products of different bonds are independent of one another
+ * and run on the library's side streams while the chain continues; the caller's stream waits for them before the
+ * call's work counts as done.
+ * mpdo_bond_env_step: one step of the right-to-left sweep on the un-canonicalised state. M0 = M_out[j] [B,l,2,a,r0],
+ * W [B,r0,rw] (state dtype) what the previous step returned for the right index (NULL at the last site), Ci the
+ * left inverse of bond j. With M = M0.W = U S V^h the reference's two-site matrix is Q.M for an isometry Q:
+ * T_out = sqrt(S_k) V_k^h [B,k,2,a,rw], W_out = Ci^h U_k sqrt(S_k) [B,l,k] (to be applied to the right index of site
+ * j-1: by the next step, or directly for site 0), sv_out (optional, [B,l]) the squared singular values.
+ * Replaces: tn.split_node_qr / tn.contract_between / tn.split_node at TNNOptimizer.py:98-106 and :126-133
+ * (bondTruncate, TNNOptimizer.py:72-84). */
+int mpdo_env_sweep(int dtype, int B, int nsites, const int* l, const int* a, const int* r, const void* const* T,
+                   void* const* Ci_out, void* const* M_out, void* stream);
+int mpdo_bond_env_step(int dtype, int B, int l, int a, int r0, const void* M0, int rw, const void* W, const void* Ci,
+                       int k, void* T_out, void* W_out, double* sv_out, void* stream);
+
 /* Inner-index truncation T [B,l,2,a,r] -> U.S [B,l,2,k',r], k = min(kappa, a) (k = a for kappa = None); max_err and
  * k_out as above (TNNOptimizer.py:189 passes max_truncation_err with relative=True). disc_out (optional, [B] doubles)
  * = norm of the discarded part. SYNC when the top-k subspace iteration is used (max_err < 0, a >= 64 and a >= 8k) or

@@ -7,7 +7,7 @@ import torch
 from MPDOSimulator._engine.steps import Engine
 
 
-def run_engine(oc, prims, dtype, device='cpu', npass=None):
+def run_engine(oc, prims, dtype, device='cpu', npass=None, env_sweep=False):
     E = Engine(prims, dtype, npass)
     n = oc.qn
     Ts = [torch.tensor([1, 0], dtype=dtype, device=device).reshape(1, 1, 2, 1, 1) for _ in range(n)]
@@ -17,8 +17,11 @@ def run_engine(oc, prims, dtype, device='cpu', npass=None):
         if layer[0] == 'truncate':
             if n <= 1 or all(bond):
                 if not (oc.chi is None and oc.max_truncation_err is None):
-                    E.qr_left2right(Ts)
-                    E.svd_right2left(Ts, oc.chi, oc.max_truncation_err)
+                    if env_sweep and oc.max_truncation_err is None:
+                        E.bond_truncate_env(Ts, oc.chi)
+                    else:
+                        E.qr_left2right(Ts)
+                        E.svd_right2left(Ts, oc.chi, oc.max_truncation_err)
                 if not oc.ideal and not (oc.kappa is None and oc.max_truncation_err is None):
                     E.svd_kappa(Ts, oc.kappa, oc.max_truncation_err, inner)
         elif layer[0] == 'barrier':

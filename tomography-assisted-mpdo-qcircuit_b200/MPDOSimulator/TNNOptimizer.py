@@ -38,8 +38,39 @@ def bondTruncate(_qubits: List[DenseNode], max_singular_values: Optional[int] = 
     """QR sweep left-to-right, then SVD truncation right-to-left (TNNOptimizer.py:72-84)."""
     if max_singular_values is None and max_truncation_err is None and not regularization:
         return None
+    if _use_env_form(_qubits, max_singular_values, max_truncation_err):
+        eng = _engine_of(_qubits)
+        Ts = [q.data for q in _qubits]
+        eng.bond_truncate_env(Ts, max_singular_values)
+        for q, t in zip(_qubits, Ts):
+            q.data = t
+        return None
     qr_left2right(_qubits)
     svd_right2left(_qubits, max_singular_values=max_singular_values, max_truncation_err=max_truncation_err)
+
+
+ENV_FORM_MAX_BATCH = 4
+
+
+def _use_env_form(_qubits, max_singular_values, max_truncation_err):
+    """The environment form of bondTruncate (_engine/steps.py bond_truncate_env: the QR sweep becomes a chain of
+    contractions plus mutually independent factorisations, leaving the right-to-left sweep as the only sequential chain
+    of decompositions) is taken for complex64 states with a fixed chi and few circuits per call, where a layer is bound
+    by the latency of dependent factorisations. Large batches are bound by throughput instead, and there the fp64
+    environment contractions cost more than the fp32 products of the QR sweep. Same results either way
+    (tests/test_env_sweep.py, tests/test_gpu_env_sweep.py). MPDO_ENV_SWEEP=0 / 1 forces the choice."""
+    import os
+    import torch
+    if max_singular_values is None or max_truncation_err is not None or len(_qubits) < 2:
+        return False
+    if not all(q.has_right for q in _qubits[:-1]) or _qubits[0].data.shape[1] != 1:
+        return False      # the two-sweep form raises the reference's error for a missing bond
+    if _qubits[0].data.dtype != torch.complex64:
+        return False
+    knob = os.environ.get('MPDO_ENV_SWEEP')
+    if knob is not None:
+        return knob == '1'
+    return max(q.data.shape[0] for q in _qubits) <= ENV_FORM_MAX_BATCH
 
 
 def qr_left2right(_qubits: List[DenseNode]):

@@ -54,6 +54,10 @@ SYMBOLS = {
     'mpdo_bond_svd_step': (C.c_int, [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double,
                                                     C.POINTER(C.c_int), C.c_void_p, C.c_void_p, C.c_void_p,
                                                     C.c_void_p]),
+    'mpdo_env_sweep': (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
+    'mpdo_bond_env_step': (C.c_int, [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'mpdo_kappa_truncate': (C.c_int, [C.c_int] * 5 + [C.c_void_p, C.c_int, C.c_double, C.POINTER(C.c_int), C.c_void_p,
                                                      C.c_void_p, C.c_void_p]),
     'mpdo_split_2q': (C.c_int, [C.c_int] * 6 + [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p,

@@ -71,6 +71,46 @@ class NativeEngine(Engine):
         disc = sv[:, k:].clamp_min(0).sqrt() if self.npass == 1 else sv[:, k:]
         return Tl_n, Tr_n, disc
 
+    def bond_truncate_env(self, Ts, chi):
+        """steps.Engine.bond_truncate_env as two kinds of library calls: mpdo_env_sweep (environment chain on the
+        current stream, the factorisations of all bonds on the library's side streams) and one mpdo_bond_env_step per
+        bond, right to left. No host synchronisation."""
+        n = len(Ts)
+        if n < 2:
+            return []
+        Ts[:] = [t.contiguous() for t in Ts]
+        Bn = Ts[0].shape[0]
+        dev = Ts[0].device
+        if Ts[0].shape[1] != 1:
+            raise ValueError('the first site must have a trivial left bond')
+        ls = (C.c_int * n)(*[t.shape[1] for t in Ts])
+        as_ = (C.c_int * n)(*[t.shape[3] for t in Ts])
+        rs = (C.c_int * n)(*[t.shape[4] for t in Ts])
+        Cis = [None] + [torch.empty((Bn, t.shape[1], t.shape[1]), dtype=torch.complex128, device=dev) for t in Ts[1:]]
+        Ms = [None] + [torch.empty_like(t) for t in Ts[1:]]
+        tp = (C.c_void_p * n)(*[t.data_ptr() for t in Ts])
+        cip = (C.c_void_p * n)(*[None if c is None else c.data_ptr() for c in Cis])
+        mp = (C.c_void_p * n)(*[None if m is None else m.data_ptr() for m in Ms])
+        self._call('mpdo_env_sweep', self.lib.mpdo_env_sweep, self.dt, Bn, n, ls, as_, rs, tp, cip, mp, _stream())
+        W, disc = None, []
+        for idx in range(n - 1, 0, -1):
+            M0 = Ms[idx]
+            _, l, _, a, r0 = M0.shape
+            rw = r0 if W is None else W.shape[2]
+            k = l if chi is None else min(int(chi), l)
+            T_n = torch.empty((Bn, k, 2, a, rw), dtype=M0.dtype, device=dev)
+            W_n = torch.empty((Bn, l, k), dtype=M0.dtype, device=dev)
+            sv = torch.empty((Bn, l), dtype=torch.float64, device=dev)
+            self._call('mpdo_bond_env_step', self.lib.mpdo_bond_env_step, self.dt, Bn, l, a, r0, _p(M0), rw,
+                       None if W is None else _p(W), _p(Cis[idx]), k, _p(T_n), _p(W_n), _p(sv), _stream())
+            Ts[idx], W = T_n, W_n
+            disc.append(sv[:, k:].clamp_min(0).sqrt())
+        T0 = Ts[0]
+        out = torch.empty(tuple(T0.shape[:4]) + (W.shape[2],), dtype=T0.dtype, device=dev)
+        self.p.contract(T0, (1, 3, 1), W, (1, 1, 1), out, (1, 3, 1))
+        Ts[0] = out
+        return disc
+
     def kappa_truncate(self, T, kappa, max_err=None):
         T = T.contiguous()
         Bn, l, _, a, r = T.shape

@@ -363,6 +363,93 @@ class Engine:
         return Tl_n, Tr_n, disc
 
     # ------------------------------------------------------------------------------------------
+    # R4 + R5 through left environments (complex64 states): the same truncation, one sequential sweep instead of two
+    # ------------------------------------------------------------------------------------------
+    def env_step(self, E, T):
+        """E [B,l,l] (complex128) = A^h A of the block left of the bond, T [B,l,2,a,r] ->
+        E'[r,r'] = sum conj(T[l,s,a,r]) E[l,l'] T[l',s,a,r'] (the same matrix the QR sweep forms as the Gram matrix of
+        R.T, TNNOptimizer.py:87-108, without the factorisation in between)."""
+        p = self.p
+        Bn, l, _, a, r = T.shape
+        X = torch.empty((Bn, l, 2, a, r), dtype=C128, device=T.device)
+        p.contract(E, (1, 1, 1), T, (1, 1, 3), X, (1, 1, 3))
+        En = torch.empty((Bn, r, r), dtype=C128, device=T.device)
+        p.contract(T.permute(0, 4, 1, 2, 3), (1, 1, 3), X, (1, 3, 1), En, (1, 1, 1), conjA=True)
+        return En
+
+    def env_factor(self, E):
+        """E = C^h C and the left inverse Ci (Ci . C^h = 1 on the numerical range): the R of the QR sweep up to a
+        unitary from the left, which no later quantity depends on."""
+        p = self.p
+        if hasattr(p, 'chol_psd') and not os.environ.get('MPDO_NO_CHOLQR'):
+            try:
+                Lh, Linv, _ = p.chol_psd(E, self.null_tol)
+                return Lh, Linv
+            except RuntimeError:      # shape not schedulable: eigen route
+                pass
+        lam, Vh = p.eigh_psd(E, self.jacobi_tol, rank_revealing=self._rr(E))
+        n = E.shape[1]
+        return (p.rowscale(Vh, lam, n, 0.5, self.null_tol, 0, C128), p.rowscale(Vh, lam, n, -0.5, self.null_tol, 0, C128))
+
+    def bond_env_step(self, M0, W, Ci, chi):
+        """One step of the right-to-left chi truncation on the un-canonicalised state. M0 [B,l,2,a,r0] = C . T is the
+        site right of the bond times the factor of the bond's left environment, W [B,r0,r] what the previous step left
+        for the right index (None at the last site), Ci the left inverse of the factor. With M = M0 . W the two-site
+        matrix of the reference (TNNOptimizer.py:111-134) is Q . M for an isometry Q, so its truncated SVD is
+        Q U | S | V^h with M = U S V^h: returns (sqrt(S_k) V_k^h [B,k,2,a,r], W' = C^+ U_k sqrt(S_k) [B,l,k],
+        discarded values)."""
+        p = self.p
+        Bn, l, _, a, _ = M0.shape
+        if W is not None:
+            M = self._empty((Bn, l, 2, a, W.shape[2]), M0)
+            p.contract(M0, (1, 3, 1), W, (1, 1, 1), M, (1, 3, 1))
+        else:
+            M = M0
+        r = M.shape[4]
+        G = self._gram_rows(M, (1, 1, 3))
+        lam, Uh = p.eigh_psd(G, self.jacobi_tol, rank_revealing=self._rr(G))
+        k = l if chi is None else min(int(chi), l)
+        disc = lam[:, k:].clamp_min(0).sqrt()
+        T_n = self._empty((Bn, k, 2, a, r), M0)
+        p.contract(p.rowscale(Uh, lam, k, -0.25, self.null_tol, 0, self.dtype), (1, 1, 1), M, (1, 1, 3), T_n, (1, 1, 3))
+        UL = p.rowscale(Uh, lam, k, 0.25, self.null_tol, 0, C128)               # sqrt(s_j) conj(U[i, j])
+        W_n = self._empty((Bn, l, k), M0)                                        # sum_i conj(Ci[i,i']) conj(UL[j,i])
+        p.contract(Ci.permute(0, 2, 1), (1, 1, 1), UL.permute(0, 2, 1), (1, 1, 1), W_n, (1, 1, 1), conjA=True, conjB=True)
+        return T_n, W_n, disc
+
+    def bond_truncate_env(self, Ts, chi):
+        """bondTruncate (QR sweep + chi sweep, TNNOptimizer.py:72-134) for complex64 states with a fixed chi, in place
+        on the list of site tensors. The left-to-right pass only chains the environments E_i (contractions); their
+        factorisations are independent of one another; the right-to-left pass is the only sequential chain of
+        decompositions left. Same singular values and the same sqrt(S) | sqrt(S) split at every bond as the two-sweep
+        form (the factors differ from its R by unitaries that cancel)."""
+        p = self.p
+        n = len(Ts)
+        if n < 2:
+            return []
+        Bn = Ts[0].shape[0]
+        E = torch.ones((Bn, 1, 1), dtype=C128, device=Ts[0].device)
+        if Ts[0].shape[1] != 1:
+            raise ValueError('the first site must have a trivial left bond')
+        factors = [None] * n
+        for i in range(n - 1):
+            E = self.env_step(E, Ts[i])
+            C, Ci = self.env_factor(E)
+            M0 = self._empty(tuple(Ts[i + 1].shape), Ts[i + 1])      # C . T of the site right of the bond: independent
+            p.contract(C.to(self.dtype), (1, 1, 1), Ts[i + 1], (1, 1, 3), M0, (1, 1, 3))     # of the sweep that follows
+            factors[i + 1] = (M0, Ci)
+        W, disc = None, []
+        for idx in range(n - 1, 0, -1):
+            M0, Ci = factors[idx]
+            Ts[idx], W, d = self.bond_env_step(M0, W, Ci, chi)
+            disc.append(d)
+        T0 = Ts[0]
+        out = self._empty(tuple(T0.shape[:4]) + (W.shape[2],), T0)
+        p.contract(T0, (1, 3, 1), W, (1, 1, 1), out, (1, 3, 1))
+        Ts[0] = out
+        return disc
+
+    # ------------------------------------------------------------------------------------------
     # R3: inner-index (kappa) truncation                 TNNOptimizer.py:164-197
     # ------------------------------------------------------------------------------------------
     def eigh_topk(self, G, k, max_iter=None):

@@ -719,6 +719,157 @@ extern "C" int mpdo_bond_svd_step(int dtype, int npass, int B, int lp, int ap, i
   return contract(c.st, TL, {1, 3, 1}, transposed(left), {1, 1, 1}, TLo, {1, 3, 1}, false, true);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// bondTruncate through left environments (complex64 states, fixed chi): see MPDOSimulator/_engine/steps.py
+// bond_truncate_env for the mathematics. The left-to-right pass is a chain of contractions (E_{i+1} = T_i^h E_i T_i,
+// the very Gram matrix the QR sweep forms); the factorisations E_i = C_i^h C_i do not depend on one another and run on
+// side streams while the chain continues; the right-to-left pass (mpdo_bond_env_step) is the one sequential chain of
+// decompositions left.
+// ---------------------------------------------------------------------------------------------------
+constexpr int N_SIDE = 8;
+static std::mutex g_side_mu;
+static cudaStream_t g_side[64][N_SIDE] = {{nullptr}};
+
+static cudaStream_t side_stream(int i) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  cudaStream_t& s = g_side[dev][i % N_SIDE];
+  if (!s && cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    s = nullptr;
+  }
+  return s;
+}
+
+// E = C^h C with the left inverse Ci (written to the caller's buffer) and the product M = C . Tnext of the factor with
+// the site right of the bond, all on stream `on`
+static int env_factor(int dtype, int B, int n, const Tn& E, const Tn& Tnext, void* Ci_out, void* M_out,
+                      cudaStream_t on) {
+  Ctx cs(on, dtype, 1);
+  cs.set_batch(B);
+  Tn Cf = cs.ar.alloc(MPDO_C128, {(long long)B, (long long)n, (long long)n});
+  Tn Cd = cs.ar.alloc(dtype, {(long long)B, (long long)n, (long long)n});
+  ARENA_OK(cs);
+  int rc = MPDO_ENOSMEM;
+  if (cs.use_chol) {
+    void* scratch = cs.ar.raw((size_t)mpdo_chol_psd_scratch_bytes(B, n));
+    ARENA_OK(cs);
+    rc = mpdo_chol_psd(B, n, E.p, scratch, Cf.p, Ci_out, nullptr, cs.null_tol, on);
+    if (rc != 0 && rc != MPDO_ENOSMEM) return rc;
+  }
+  if (rc == MPDO_ENOSMEM) {   // shape not schedulable for the Cholesky kernels: eigen route
+    double* lam;
+    Tn Vh, Cis;
+    EC(eigh(cs, E, &lam, &Vh));
+    EC(rowscale(cs, Vh, lam, n, n, 0.5, cs.null_tol, 0, MPDO_C128, &Cf));
+    EC(rowscale(cs, Vh, lam, n, n, -0.5, cs.null_tol, 0, MPDO_C128, &Cis));
+    MPDO_CUDA(cudaMemcpyAsync(Ci_out, Cis.p, sizeof(double2) * (size_t)B * n * n, cudaMemcpyDeviceToDevice, on));
+  }
+  EC(copy_view(on, Cf, Cd));
+  Tn Mo = Tn::contig(M_out, dtype, {Tnext.sh[0], Tnext.sh[1], Tnext.sh[2], Tnext.sh[3], Tnext.sh[4]});
+  return contract(on, Cd, {1, 1, 1}, Tnext, {1, 1, 3}, Mo, {1, 1, 3});
+}
+
+extern "C" int mpdo_env_sweep(int dtype, int B, int nsites, const int* l, const int* a, const int* r,
+                              const void* const* T, void* const* Ci_out, void* const* M_out, void* stream) {
+  if (nsites < 2) return 0;
+  if (!l || !a || !r || !T || !Ci_out || !M_out) return fail(MPDO_EINVAL, "mpdo_env_sweep: null argument");
+  if (l[0] != 1) return fail(MPDO_EINVAL, "mpdo_env_sweep: the first site must have a trivial left bond");
+  cudaStream_t st = (cudaStream_t)stream;
+  Ctx c(st, dtype, 1);
+  c.set_batch(B);
+  static const bool serial = getenv("MPDO_ENV_SERIAL") != nullptr;   // A/B knob: factorisations on the caller's stream
+  bool used[N_SIDE] = {false};
+  Tn E;
+  int rc = 0;
+  for (int i = 0; i + 1 < nsites && rc == 0; ++i) {
+    if (i > 0 && l[i] != r[i - 1]) {
+      rc = fail(MPDO_EINVAL, "mpdo_env_sweep: bond dimensions of neighbouring sites differ");
+      break;
+    }
+    Tn Ti = Tn::contig((void*)T[i], dtype, {(long long)B, (long long)l[i], 2, (long long)a[i], (long long)r[i]});
+    Tn En;
+    if (i == 0) {
+      rc = gram_cols(c, Ti, {1, 3, 1}, &En);   // E_0 = 1
+    } else {
+      Ctx cx(st, dtype, 1);   // the wide intermediate is released as soon as the two contractions are queued
+      Tn X = cx.ar.alloc(MPDO_C128, {(long long)B, (long long)l[i], 2, (long long)a[i], (long long)r[i]});
+      En = c.ar.alloc(MPDO_C128, {(long long)B, (long long)r[i], (long long)r[i]});
+      if (cx.ar.err || c.ar.err) {
+        rc = cx.ar.err ? cx.ar.err : c.ar.err;
+        break;
+      }
+      rc = contract(st, E, {1, 1, 1}, Ti, {1, 1, 3}, X, {1, 1, 3});
+      if (rc == 0) rc = contract(st, Ti.permute({0, 4, 1, 2, 3}), {1, 1, 3}, X, {1, 3, 1}, En, {1, 1, 1}, true, false);
+    }
+    if (rc) break;
+    E = En;
+    // cooperative factorisations (n > 256: device-wide barrier) keep to the caller's stream
+    cudaStream_t side = (serial || r[i] > 256) ? nullptr : side_stream(i);
+    if (side) {
+      cudaEvent_t ev;
+      MPDO_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      cudaEventRecord(ev, st);
+      cudaStreamWaitEvent(side, ev, 0);
+      cudaEventDestroy(ev);
+      used[i % N_SIDE] = true;
+    }
+    if (l[i + 1] != r[i]) {
+      rc = fail(MPDO_EINVAL, "mpdo_env_sweep: bond dimensions of neighbouring sites differ");
+      break;
+    }
+    Tn Tnext = Tn::contig((void*)T[i + 1], dtype,
+                          {(long long)B, (long long)l[i + 1], 2, (long long)a[i + 1], (long long)r[i + 1]});
+    rc = env_factor(dtype, B, r[i], E, Tnext, Ci_out[i + 1], M_out[i + 1], side ? side : st);
+  }
+  for (int s = 0; s < N_SIDE; ++s) {   // join (also on failure: the arena of `c` is freed on `st` after this)
+    if (!used[s]) continue;
+    cudaEvent_t ev;
+    if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      cudaStreamSynchronize(side_stream(s));
+      continue;
+    }
+    cudaEventRecord(ev, side_stream(s));
+    cudaStreamWaitEvent(st, ev, 0);
+    cudaEventDestroy(ev);
+  }
+  return rc;
+}
+
+// One step of the right-to-left chi truncation on the un-canonicalised state: M0 [B,l,2,a,r0] = C . T (the site right
+// of the bond times the factor of the bond's environment, from mpdo_env_sweep), W [B,r0,rw] (state dtype; NULL at the
+// last site, then rw = r0), Ci [B,l,l] complex128.
+// M = M0 . W = U S V^h  ->  T_out = sqrt(S_k) V_k^h [B,k,2,a,rw], W_out = Ci^h U_k sqrt(S_k) [B,l,k],
+// sv_out (optional) the l squared singular values.
+extern "C" int mpdo_bond_env_step(int dtype, int B, int l, int a, int r0, const void* M0, int rw, const void* W,
+                                  const void* Ci, int k, void* T_out, void* W_out, double* sv_out, void* stream) {
+  Ctx c((cudaStream_t)stream, dtype, 1);
+  c.set_batch(B);
+  if (k < 1 || k > l) return fail(MPDO_EINVAL, "mpdo_bond_env_step: kept rank out of range");
+  const long long Bn = B;
+  Tn M = Tn::contig((void*)M0, dtype, {Bn, l, 2, a, r0});
+  if (W) {
+    Tn MW = c.ar.alloc(dtype, {Bn, (long long)l, 2, (long long)a, (long long)rw});
+    ARENA_OK(c);
+    EC(contract(c.st, M, {1, 3, 1}, Tn::contig((void*)W, dtype, {Bn, r0, rw}), {1, 1, 1}, MW, {1, 3, 1}));
+    M = MW;
+  } else {
+    rw = r0;
+  }
+  WideSvd w;
+  EC(svd_wide(c, M, {1, 1, 3}, &w));
+  if (sv_out)
+    MPDO_CUDA(cudaMemcpyAsync(sv_out, w.sv, sizeof(double) * (size_t)B * w.n, cudaMemcpyDeviceToDevice, c.st));
+  Tn right, UL;
+  EC(wide_right(c, w, k, dtype, &right));
+  EC(contract(c.st, right, {1, 1, 1}, M, {1, 1, 3}, Tn::contig(T_out, dtype, {Bn, k, 2, a, rw}), {1, 1, 3}));
+  EC(wide_left(c, w, k, MPDO_C128, &UL));   // UL[j,i] = sqrt(s_j) conj(U[i,j])
+  return contract(c.st, transposed(Tn::contig((void*)Ci, MPDO_C128, {Bn, l, l})), {1, 1, 1}, transposed(UL),
+                  {1, 1, 1}, Tn::contig(W_out, dtype, {Bn, l, k}), {1, 1, 1}, true, true);
+}
+
 // kappa truncation: k = min(kappa, a), further reduced by the relative-error rule when max_err >= 0 (SYNC; the output
 // is written densely with the kept rank). disc_out[b] = norm of the discarded part.
 extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const void* T, int k, double max_err,
@@ -734,21 +885,47 @@ extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const 
   bool done = false;
   // The subspace iteration pays off when the spectrum has a gap after the kept values; on workloads where the cut sits
   // in a cluster (the equal-weight error branches of a chi-matrix gate) it stalls every time and costs two wasted
-  // iterations (~1.5 ms of 6.5 at a = 1024). Remember the outcome per (a, k): after a stall the next 15 calls with that
-  // signature go straight to the full rank-revealing decomposition, the 16th probes again. Both routes are exact
-  // solvers run to convergence, so this only moves time.
-  static std::atomic<int> topkSkip[64];
-  std::atomic<int>& skip = topkSkip[((unsigned)a * 31u + (unsigned)k) & 63u];
+  // iterations (~2.2 ms of 2.7 at a = 64 on the headline workload). Remember the outcome per (a, k): after a stall the
+  // next 15 calls with that signature go straight to the full rank-revealing decomposition and ONE caller probes again
+  // (the sites of a layer arrive here from a dozen strand threads at once: letting every one of them probe cost 7 ms
+  // per layer); every further stall quadruples the pause (15, 63, 255 ... 4095 calls), a converged probe resets it.
+  // Both routes are exact solvers run to convergence, so this only moves time.
+  static std::atomic<int> topkSkip[64], topkStalls[64];
+  const unsigned slot = ((unsigned)a * 31u + (unsigned)k) & 63u;
+  std::atomic<int>& skip = topkSkip[slot];
+  std::atomic<int>& stalls = topkStalls[slot];
   bool tryTopk = max_err < 0 && a >= 64 && a >= 8 * k;
-  if (tryTopk && skip.load(std::memory_order_relaxed) > 0) {
-    skip.fetch_sub(1, std::memory_order_relaxed);
-    tryTopk = false;
+  if (tryTopk) {
+    int cur = skip.load(std::memory_order_relaxed);
+    for (;;) {
+      if (cur > 0) {            // paused: one call less to wait
+        if (skip.compare_exchange_weak(cur, cur - 1, std::memory_order_relaxed)) {
+          tryTopk = false;
+          break;
+        }
+      } else if (cur == 0) {    // claim the probe (-1 while it runs)
+        if (skip.compare_exchange_weak(cur, -1, std::memory_order_relaxed)) break;
+      } else {                  // another thread is probing right now
+        tryTopk = false;
+        break;
+      }
+    }
   }
   if (tryTopk) {
     Tn Vt;
     int conv = 0;
-    EC(eigh_topk(c, G, k, &theta, &Vt, &conv));
-    skip.store(conv ? 0 : 15, std::memory_order_relaxed);
+    const int rcTop = eigh_topk(c, G, k, &theta, &Vt, &conv);
+    if (rcTop != 0) {
+      skip.store(0, std::memory_order_relaxed);
+      return rcTop;
+    }
+    if (conv) {
+      stalls.store(0, std::memory_order_relaxed);
+      skip.store(0, std::memory_order_relaxed);
+    } else {
+      const int n = std::min(stalls.fetch_add(1, std::memory_order_relaxed), 4);
+      skip.store((16 << (2 * n)) - 1, std::memory_order_relaxed);
+    }
     if (conv) {
       thetaStride = (int)Vt.sh[1];
       Tn Vk = c.ar.alloc(dtype, {(long long)B, (long long)k, (long long)a});

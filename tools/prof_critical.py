@@ -13,12 +13,13 @@ from MPDOSimulator import _engine
 n = bench.N_QUBITS
 files = {'CZ': {f'{i}{i + 1}': bench.chi_file() for i in range(n - 1)}, 'CP': {}}
 angles = bench.layer_angles(0, depth=14)
+LAYER = int(os.environ.get('LAYER', '11'))
 circs = []
 for d in range(13):
     c = Simulator.TensorCircuit(qn=n, ideal=False, noiseType='realNoise', chiFileDict=files, chi=bench.CHI, kappa=bench.KAPPA, chip='best', dtype=torch.complex64, device='cuda:0')
     bench.add_layer(c, d, angles); circs.append(c)
 state = Simulator.Tools.create_ket0Series(n, dtype=torch.complex64)
-for d in range(11):
+for d in range(LAYER):
     circs[d].evolve(state)
 eng = _engine.engine_for(torch.complex64)
 log = []
@@ -36,7 +37,7 @@ def wrap(name):
 for nm in ('split_2q', 'qr_step', 'bond_svd_step', 'kappa_truncate', 'absorb_1q'):
     wrap(nm)
 torch.cuda.synchronize(); t0 = time.perf_counter()
-circs[11].evolve(state)
+circs[LAYER].evolve(state)
 torch.cuda.synchronize(); tot = 1e3 * (time.perf_counter() - t0)
 agg = collections.OrderedDict()
 for name, dt, shp, out in log:

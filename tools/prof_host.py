@@ -58,3 +58,23 @@ for d in (11, 12):
     marks.clear()
     circs[d].evolve(state)
     print('layer %d phases (host issue / total ms):' % d, ', '.join('%s %.1f / %.1f' % m for m in marks if m[2] > 0.05))
+
+# per library call, serialised (a synchronize on both sides of every step call of the truncation sweeps)
+from MPDOSimulator import _engine
+eng = _engine.engine_for(torch.complex64)
+acc = {}
+orig_call = eng._call
+def call(what, fn, *a):
+    if what in ('mpdo_split_2q', 'mpdo_kappa_truncate'):
+        return orig_call(what, fn, *a)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    r = orig_call(what, fn, *a)
+    torch.cuda.synchronize(); dt = 1e3 * (time.perf_counter() - t0)
+    acc.setdefault(what, []).append(dt)
+    return r
+eng._call = call
+restore()
+for d in (11, 12):
+    acc.clear()
+    circs[d].evolve(state)
+    print('layer %d sweep calls:' % d, {k: (len(v), round(sum(v), 2), [round(x, 2) for x in v[:24]]) for k, v in acc.items()})
