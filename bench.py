@@ -46,6 +46,8 @@ for _p in (ROOT, PKG):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
+os.environ.setdefault('CUDA_MODULE_LOADING', 'EAGER')   # see MPDOSimulator/__init__.py (must precede CUDA initialisation)
+
 import torch  # noqa: E402
 
 N_QUBITS, CHI, KAPPA, DEPTH = 20, 64, 4, 20

@@ -204,6 +204,7 @@ def test_cz_pair_fusion_matches_one_split_per_gate(monkeypatch):
     n = 4
     files = {'CZ': {f'{i}{i + 1}': os.path.join(CHI_DIR, 'czDefault.mat') for i in range(n - 1)}, 'CP': {}}
     kw = dict(ideal=False, noiseType='realNoise', chiFileDict=files, chi=8, kappa=3, chip='best')
+    monkeypatch.setenv('MPDO_GROUPING', '0')     # count one split call per pair (same-shape pairs are stacked otherwise)
 
     def run(dtype):
         c = Simulator.TensorCircuit(qn=n, dtype=dtype, device='cpu', **kw)

@@ -415,16 +415,18 @@ class TensorCircuit(QuantumCircuit):
         _, programs, noisy2q = entry
         self.last_stats['noisy_2q_updates'] = self.last_stats.get('noisy_2q_updates', 0) + noisy2q
 
-        # Strands are issued concurrently, one CUDA stream each. With MPDO_GROUPING=1 strands whose step sequences
-        # and tensor shapes coincide (the bulk brick pairs of a layer) are instead stacked along the batch axis and run
-        # as ONE launch sequence. Measured on B200 (profiles/r2_grouping.md): half the launches, but no faster on cfg2
-        # (148 vs 143 ms per layer) and slower on cfg4 (8.4 vs 12.9 circuits/s: one stream serialises the Gram
-        # contractions of one pair behind the factorisations of another, and a batch-wide stall of the top-kappa
-        # iteration sends every member down the full decomposition) - so it is opt-in.
+        # Strands are issued concurrently, one CUDA stream each; strands whose step sequences and tensor shapes coincide
+        # (the bulk brick pairs of a layer) are stacked along the batch axis and run as ONE launch sequence when the
+        # circuit batch is small (_engine.grouping_enabled: a third fewer launches and 5 % per cfg2 layer; for large
+        # batches one stream serialises the Gram contractions of one pair behind the factorisations of another and
+        # separate streams win - cfg4 8.4 vs 12.9 circuits/s, profiles/r2_grouping.md).
         cuda = getattr(_engine.get_prims(), 'name', '') == 'cuda'
+        batch = max([s.data.shape[0] for s in state] +
+                    [st[-3 if st[0] == '2q' else -2].shape[0] for _, steps in programs for st in steps])
+        grouped = _engine.grouping_enabled(batch)
         groups = {}
         for prog in programs:
-            key = self._signature(state, prog) if os.environ.get('MPDO_GROUPING', '0') == '1' else id(prog)
+            key = self._signature(state, prog) if grouped else id(prog)
             groups.setdefault(key, []).append(prog)
         parallel = cuda and len(groups) > 1
 

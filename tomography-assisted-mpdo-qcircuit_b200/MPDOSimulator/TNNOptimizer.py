@@ -138,7 +138,7 @@ def svdKappa_left2right(_qubits: List[DenseNode], max_singular_values: Optional[
     groups = {}
     for q in todo:
         # (not with the relative-error rule: its kept rank is per site, and a stacked call pads to the group maximum)
-        key = (tuple(q.data.shape) if os.environ.get('MPDO_GROUPING', '0') == '1' and max_truncation_err is None
+        key = (tuple(q.data.shape) if _engine.grouping_enabled(q.data.shape[0]) and max_truncation_err is None
                else id(q))
         groups.setdefault(key, []).append(q)
 

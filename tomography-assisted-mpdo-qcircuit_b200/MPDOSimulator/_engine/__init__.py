@@ -31,3 +31,20 @@ def engine_for(dtype):
         else:
             _ENGINES[key] = Engine(p, dtype)          # the same sequences over the Python primitive wrappers
     return _ENGINES[key]
+
+
+GROUPING_MAX_BATCH = 4
+
+
+def grouping_enabled(batch):
+    """Whether same-shape strands (the bulk brick pairs of a layer, the per-site inner-index truncations) are stacked
+    along the batch axis and run as ONE launch sequence instead of one CUDA stream each. For a single circuit (or a
+    few) the layer is bound by launch and synchronisation latency and stacking wins (cfg2: 36.2 -> 34.3 ms per layer,
+    a third fewer launches); for large parameter-sweep batches every launch already fills the device and one stream
+    only serialises what separate streams overlap (cfg4: 8.4 vs 12.9 circuits/s, profiles/r2_grouping.md).
+    MPDO_GROUPING=0 / 1 forces the choice."""
+    import os
+    knob = os.environ.get('MPDO_GROUPING')
+    if knob is not None:
+        return knob == '1'
+    return int(batch) <= GROUPING_MAX_BATCH

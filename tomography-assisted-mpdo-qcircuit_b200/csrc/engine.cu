@@ -11,6 +11,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 #include <atomic>
 
 #include "engine.cuh"
@@ -375,13 +376,10 @@ static int keep_rank(Ctx& c, double* sv, int B, int n, bool squared, int cap, do
   int32_t* dk = (int32_t*)c.ar.raw(sizeof(int32_t) * (size_t)B);
   ARENA_OK(c);
   EC(mpdo_rank_rule(B, n, sv, n, squared, cap, max_err, relative, c.f32, dk, 1, c.st));
-  static thread_local int32_t* hk = nullptr;
-  static thread_local int hcap = 0;
-  if (hcap < B) {
-    if (hk) cudaFreeHost(hk);
-    MPDO_CUDA(cudaMallocHost(&hk, sizeof(int32_t) * (size_t)B));
-    hcap = B;
-  }
+  // (pageable on purpose: cudaMallocHost from a strand thread while persistent kernels of other strands are running
+  // was measured to stall the caller for 40-150 ms - a single slow step per process - and the read-back is a few bytes)
+  std::vector<int32_t> hkv((size_t)B);
+  int32_t* hk = hkv.data();
   MPDO_CUDA(cudaMemcpyAsync(hk, dk, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, c.st));
   MPDO_CUDA(cudaStreamSynchronize(c.st));
   int best = 1;
@@ -589,13 +587,8 @@ static int eigh_topk(Ctx& c, const Tn& G, int k, double** theta_out, Tn* Vt, int
   double* res = c.ar.reals(B);
   ARENA_OK(c);
   EC(contract(c.st, Yr, {1, 1, 1}, Gt, {1, 1, 1}, Zr, {1, 1, 1}));
-  static thread_local double* hres = nullptr;
-  static thread_local long long hcap = 0;
-  if (hcap < B) {
-    if (hres) cudaFreeHost(hres);
-    MPDO_CUDA(cudaMallocHost(&hres, sizeof(double) * (size_t)B));
-    hcap = B;
-  }
+  std::vector<double> hresv((size_t)B);   // pageable on purpose, see keep_rank
+  double* hres = hresv.data();
   *converged = 0;
   // Near-degenerate clusters at the cut (e.g. the equal-weight error branches of a chi-matrix gate) make the
   // iteration stall; the rank-revealing full decomposition is cheap enough that a short leash is the better policy.
@@ -886,15 +879,17 @@ extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const 
   // The subspace iteration pays off when the spectrum has a gap after the kept values; on workloads where the cut sits
   // in a cluster (the equal-weight error branches of a chi-matrix gate) it stalls every time and costs two wasted
   // iterations (~2.2 ms of 2.7 at a = 64 on the headline workload). Remember the outcome per (a, k): after a stall the
-  // next 15 calls with that signature go straight to the full rank-revealing decomposition and ONE caller probes again
+  // next 63 calls with that signature go straight to the full rank-revealing decomposition and ONE caller probes again
   // (the sites of a layer arrive here from a dozen strand threads at once: letting every one of them probe cost 7 ms
-  // per layer); every further stall quadruples the pause (15, 63, 255 ... 4095 calls), a converged probe resets it.
+  // per layer); further stalls lengthen the pause (63, 4095, 65535 calls), a converged probe resets it. A probe on a
+  // cold process was also measured to cost far more than its kernels (25-110 ms once, first process on a machine).
   // Both routes are exact solvers run to convergence, so this only moves time.
   static std::atomic<int> topkSkip[64], topkStalls[64];
   const unsigned slot = ((unsigned)a * 31u + (unsigned)k) & 63u;
   std::atomic<int>& skip = topkSkip[slot];
   std::atomic<int>& stalls = topkStalls[slot];
-  bool tryTopk = max_err < 0 && a >= 64 && a >= 8 * k;
+  static const bool noTopk = getenv("MPDO_NO_TOPK") != nullptr;   // A/B knob: always the full decomposition
+  bool tryTopk = !noTopk && max_err < 0 && a >= 64 && a >= 8 * k;
   if (tryTopk) {
     int cur = skip.load(std::memory_order_relaxed);
     for (;;) {
@@ -923,8 +918,8 @@ extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const 
       stalls.store(0, std::memory_order_relaxed);
       skip.store(0, std::memory_order_relaxed);
     } else {
-      const int n = std::min(stalls.fetch_add(1, std::memory_order_relaxed), 4);
-      skip.store((16 << (2 * n)) - 1, std::memory_order_relaxed);
+      const int n = stalls.fetch_add(1, std::memory_order_relaxed);
+      skip.store(n == 0 ? 63 : (n == 1 ? 4095 : 65535), std::memory_order_relaxed);
     }
     if (conv) {
       thetaStride = (int)Vt.sh[1];

@@ -16,6 +16,8 @@
 
 #include <cooperative_groups.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -1156,13 +1158,8 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
     }
     // SYNC (multi-launch mode only): read this sweep's rotation counters back and stop once every matrix of
     // the batch has converged, instead of enqueueing no-op rounds up to maxSweeps.
-    static thread_local int* hCnt = nullptr;
-    static thread_local int hCap = 0;
-    if (hCap < batch) {
-      if (hCnt) cudaFreeHost(hCnt);
-      MPDO_CUDA(cudaMallocHost(&hCnt, sizeof(int) * (size_t)batch));
-      hCap = batch;
-    }
+    std::vector<int> hCntV((size_t)batch);   // pageable on purpose (no cudaMallocHost on a strand thread)
+    int* hCnt = hCntV.data();
     MPDO_CUDA(cudaMemcpy2DAsync(hCnt, sizeof(int), work + sw, sizeof(int) * WORK_INTS, sizeof(int), batch,
                                 cudaMemcpyDeviceToHost, st));
     MPDO_CUDA(cudaStreamSynchronize(st));
