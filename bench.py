@@ -86,11 +86,15 @@ def add_layer(circ, d, angles, n=N_QUBITS):
 # clocks
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """nvidia-smi in loop mode, read by a thread. It is started well before the timed region (the first nvidia-smi /
+    NVML start-up of a fresh machine takes the driver's locks for a while: measured as 70-210 ms steps in the first
+    bench process of a box when it was started at the edge of the timed region) and keeps running through it; only
+    the rows read between begin() and stop() are reported."""
     FIELDS = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
               'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.t_begin = index, [], None, None
 
     def start(self):
         try:
@@ -104,20 +108,28 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        t_end = time.perf_counter()
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except subprocess.TimeoutExpired:
             self.proc.kill()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        t0 = self.t_begin if self.t_begin is not None else 0.0
+        rows = [r for t, r in self.rows if t0 <= t <= t_end + 0.25]
+        if not rows and self.rows:      # a timed region shorter than the sampling period: the sample nearest to it
+            rows = [min(self.rows, key=lambda tr: abs(tr[0] - 0.5 * (t0 + t_end)))[1]]
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in self.rows)]
+        reasons = [nm for i, nm in enumerate(names) if any(len(r) > 2 + i and r[2 + i] == 'Active' for r in rows)]
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
                 'reasons': reasons, 'samples': len(sm)}
 
@@ -340,6 +352,9 @@ def b200_arm(args):
         upd = add_layer(c, d, angles)
         return c, upd
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()       # long before the timed region (see ClockSampler); rows are filtered to the region
     circuits = [layer_circuit(d) for d in range(P + W + K)]
     state = Simulator.Tools.create_ket0Series(n, dtype=torch.complex64, device='cpu')
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
@@ -381,9 +396,8 @@ def b200_arm(args):
         s.data = snap.clone()
 
     # ---- timed region: device-resident state -----------------------------------------------------
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.begin()
     launches0 = base.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()

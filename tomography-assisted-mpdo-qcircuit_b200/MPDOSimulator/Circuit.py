@@ -327,7 +327,7 @@ class TensorCircuit(QuantumCircuit):
     def _stamp(ops):
         """Identity + in-place version of every tensor a gate of the segment holds: a compiled segment is reused
         only while its gates are the ones it was compiled from."""
-        out = []
+        out = [(os.environ.get('MPDO_NO_FUSE'), os.environ.get('MPDO_NO_KRAUS_COMPRESSION'))]   # knobs read by _program
         for _, g, oqs in ops:
             out.append((id(g), tuple(oqs)))
             for v in vars(g).values():

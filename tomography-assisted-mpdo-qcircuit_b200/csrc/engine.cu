@@ -885,12 +885,13 @@ extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const 
   // cold process was also measured to cost far more than its kernels (25-110 ms once, first process on a machine).
   // Both routes are exact solvers run to convergence, so this only moves time.
   static std::atomic<int> topkSkip[64], topkStalls[64];
-  const unsigned slot = ((unsigned)a * 31u + (unsigned)k) & 63u;
+  const unsigned slot = (((unsigned)a * 31u + (unsigned)k) * 17u + (unsigned)std::min(B, 64)) & 63u;
   std::atomic<int>& skip = topkSkip[slot];
   std::atomic<int>& stalls = topkStalls[slot];
   static const bool noTopk = getenv("MPDO_NO_TOPK") != nullptr;   // A/B knob: always the full decomposition
   bool tryTopk = !noTopk && max_err < 0 && a >= 64 && a >= 8 * k;
-  if (tryTopk) {
+  bool claimed = false;
+  if (tryTopk && stalls.load(std::memory_order_relaxed) > 0) {   // this signature stalled before: paused / one prober
     int cur = skip.load(std::memory_order_relaxed);
     for (;;) {
       if (cur > 0) {            // paused: one call less to wait
@@ -899,7 +900,10 @@ extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const 
           break;
         }
       } else if (cur == 0) {    // claim the probe (-1 while it runs)
-        if (skip.compare_exchange_weak(cur, -1, std::memory_order_relaxed)) break;
+        if (skip.compare_exchange_weak(cur, -1, std::memory_order_relaxed)) {
+          claimed = true;
+          break;
+        }
       } else {                  // another thread is probing right now
         tryTopk = false;
         break;
@@ -911,15 +915,20 @@ extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const 
     int conv = 0;
     const int rcTop = eigh_topk(c, G, k, &theta, &Vt, &conv);
     if (rcTop != 0) {
-      skip.store(0, std::memory_order_relaxed);
+      if (claimed) skip.store(0, std::memory_order_relaxed);
       return rcTop;
     }
     if (conv) {
-      stalls.store(0, std::memory_order_relaxed);
-      skip.store(0, std::memory_order_relaxed);
-    } else {
+      if (claimed) {   // the signature converges again: everybody may use the iteration
+        stalls.store(0, std::memory_order_relaxed);
+        skip.store(0, std::memory_order_relaxed);
+      }
+    } else if (claimed) {
       const int n = stalls.fetch_add(1, std::memory_order_relaxed);
-      skip.store(n == 0 ? 63 : (n == 1 ? 4095 : 65535), std::memory_order_relaxed);
+      skip.store(n <= 1 ? 63 : (n == 2 ? 4095 : 65535), std::memory_order_relaxed);
+    } else {           // first stall of a signature that converged so far (several callers may get here at once)
+      int expected = 0;
+      if (stalls.compare_exchange_strong(expected, 1, std::memory_order_relaxed)) skip.store(63, std::memory_order_relaxed);
     }
     if (conv) {
       thetaStride = (int)Vt.sh[1];

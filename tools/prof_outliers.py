@@ -81,7 +81,7 @@ for it in range(reps):
     circs[11].evolve(state)
     torch.cuda.synchronize(); tot = time.perf_counter() - t0
     sampling['on'] = False
-    if tot > 0.3 and it > 1:
+    if tot > 0.055 and it > 1:
         agg = collections.Counter()
         for (nm, stk), c in samples.items():
             agg[stk] += c
