@@ -398,6 +398,9 @@ def b200_arm(args):
     # ---- timed region: device-resident state -----------------------------------------------------
     if rank == 0:
         sampler.begin()
+    cuprof = os.environ.get('MPDO_BENCH_CUPROF') == '1'   # `ncu --profile-from-start off`: list the timed region only
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStart()
     launches0 = base.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -417,6 +420,8 @@ def b200_arm(args):
         dist.all_gather_into_tensor(gathered, readout)
     ev1.record()
     barrier()
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = base.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     secs = ev0.elapsed_time(ev1) * 1e-3

@@ -367,10 +367,11 @@ class TensorCircuit(QuantumCircuit):
         if tc.device(self.device).type == 'cuda' and tc.cuda.is_available():
             uploaded = {}
 
-            def up(G):
-                if id(G) not in uploaded:
-                    uploaded[id(G)] = self._dev(G)
-                return uploaded[id(G)]
+            def up(G):      # one device tensor per distinct operand VALUE: _run_group recognises equal operands of
+                key = (tuple(G.shape), G.dtype, G.contiguous().numpy().tobytes())   # stacked strands by identity
+                if key not in uploaded:
+                    uploaded[key] = self._dev(G)
+                return uploaded[key]
 
             programs = [(qubits, [st[:2] + (up(st[2]),) + st[3:] if st[0] == '1q' else st[:3] + (up(st[3]),) + st[4:]
                                   for st in steps]) for qubits, steps in programs]
@@ -515,7 +516,7 @@ class TensorCircuit(QuantumCircuit):
         ranks = {}
         for t, st in enumerate(steps0):
             Gs = [sts[t][-3 if st[0] == '2q' else -2] for _, sts in members]
-            if all(g.shape[0] == 1 for g in Gs) and all(g is Gs[0] or tc.equal(g, Gs[0]) for g in Gs[1:]):
+            if all(g.shape[0] == 1 for g in Gs) and all(g is Gs[0] or (not g.is_cuda and tc.equal(g, Gs[0])) for g in Gs[1:]):
                 G = Gs[0]
             else:
                 G = tc.cat([g.expand(Bmax, *g.shape[1:]) for g in Gs], dim=0)

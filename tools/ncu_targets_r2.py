@@ -1,10 +1,12 @@
 """Dev helper (GPU): one launch of each kernel that matters after round 2, at its steady-state cfg2 / cfg5 size, for
-`ncu --set full -k regex:"tc_apply|chol_small|chol_kernel|jacobi"`.
+`ncu --set full -k regex:"tc_apply|chol_small|chol_cluster|jacobi_cluster|jacobi_kernel|contract_kernel"`.
 
-  tc_apply_kernel<128,3> / <256,2>        : complex64 apply 65536 x 256 x 256, default and widest column tile
-  chol_kernel + jacobi_persistent_kernel  : preconditioned eigen-decomposition of graded 192 x 192 and 256 x 256 Gram
-                                            matrices (wide bond of the chi sweep / core of a gate split at chi = 64)
-  chol_small_kernel (+ jacobi_kernel<16>) : Cholesky-QR factor with inverse and eigen-decomposition at n = 64
+  tc_apply_kernel<128,3> / <256,2>          : complex64 apply 65536 x 256 x 256, default and widest column tile
+  chol_cluster_kernel + jacobi_cluster_kernel : preconditioned eigen-decomposition of graded 192 x 192 and 256 x 256
+                                              Gram matrices (wide bond of the chi sweep / core of a gate split at chi = 64)
+  chol_small_kernel (+ jacobi_kernel<16>)   : Cholesky factor with inverse and eigen-decomposition at n = 64
+  contract_kernel (fp64 accumulate)         : Gram matrix of a wide chi-sweep step (200 x 8192 -> 200 x 200, Hermitian)
+                                              and the environment step E.T (200 x 200 complex128 times 200 x 8192)
 """
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tomography-assisted-mpdo-qcircuit_b200'))
@@ -39,5 +41,13 @@ G64 = graded(64, 0.8)
 for _ in range(2):
     p.eigh_psd(G64, 1e-10, rank_revealing=True)
     p.chol_psd(G64)                       # with the left inverse (Cholesky-QR of the sweeps)
+torch.cuda.synchronize()
+T = torch.complex(torch.randn(1, 200, 8192, device=dev), torch.randn(1, 200, 8192, device=dev))
+Gm = torch.empty((1, 200, 200), dtype=C128, device=dev)
+E = graded(200, 0.93)
+X = torch.empty((1, 200, 8192), dtype=C128, device=dev)
+for _ in range(2):
+    p.contract(T, (1, 1, 1), T.permute(0, 2, 1), (1, 1, 1), Gm, (1, 1, 1), conjB=True, acc64=True, hermitian=True)
+    p.contract(E, (1, 1, 1), T, (1, 1, 1), X, (1, 1, 1))
 torch.cuda.synchronize()
 print('done')
