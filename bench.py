@@ -289,6 +289,9 @@ def cfg4_leg(dev, rank, world, barrier):
         return gather_readout(rows, total), c.last_stats.get('noisy_2q_updates', 0)
 
     run(build(ang_host))                      # rehearsal of the identical workload (pools, descriptor caches, NCCL)
+    import gc
+    gc.collect()
+    gc.freeze()                               # see b200_arm: no full collection inside a timed region
     barrier()
     # device-resident leg: circuit objects (gate operands) built before the clock starts
     c = build(ang_host)
@@ -368,6 +371,13 @@ def b200_arm(args):
         circuits[d][0].evolve(state)
     barrier()
     snapshot = [s.data.clone() for s in state]   # the e2e leg replays the same K layers from this state
+    # Python's cyclic collector: the ~30 circuit objects built above are a few hundred thousand tracked containers, and a
+    # full (generation 2) collection that happens to fall into a timed step walks all of them with the GIL held -
+    # measured as single 65-210 ms steps among 30 ms ones. Collect once now and move the survivors to the permanent
+    # generation; later collections only see what the steps themselves allocate.
+    import gc
+    gc.collect()
+    gc.freeze()
 
     if args.profile:   # per-kernel device-time table of one steady-state layer (not a benchmark number)
         from torch.profiler import ProfilerActivity, profile

@@ -160,6 +160,57 @@ def test_eigh_psd_rank_revealing(cuda_prims, n, rk, Bn):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('n,rk,Bn', [(17, 17, 2), (24, 9, 3), (40, 40, 2), (64, 64, 4), (64, 20, 2), (81, 81, 2), (100, 60, 3), (130, 90, 2), (192, 192, 1), (200, 33, 2), (256, 256, 1),
+                                     (256, 200, 12), (160, 120, 40)])
+def test_eigh_psd_blocked_factorisation(cuda_prims, n, rk, Bn):
+    """precondition = 2: blocked Cholesky without pivoting (rows ordered once by decreasing diagonal, null pivots
+    skipped) in front of the Jacobi phase, for Gram matrices of fp32 data. Held to what that use needs: eigenvalues
+    to 1e-12 of the largest (the same absolute bound as the pivoted route), reconstruction to 1e-12, orthonormal-or-
+    zero rows, the numerical rank; relative accuracy on the resolved spectrum to 1e-4 (1e-6 on the pivoted route)."""
+    A = rnd((Bn, n, rk), C128, 23)
+    A = A * torch.logspace(0, -5, rk, dtype=torch.float64)
+    G = A @ A.mH
+    G = 0.5 * (G + G.mH)
+    lam_g, Vh_g = cuda_prims.eigh_psd(G.cuda(), rank_revealing=2)
+    lam_g, Vh_g = lam_g.cpu(), Vh_g.cpu()
+    lam_c = torch.linalg.eigvalsh(G).flip(-1).clamp_min(0.0)
+    top = lam_c.max()
+    assert (lam_g - lam_c).abs().max() <= 1e-12 * top
+    big = lam_c > 1e-9 * top
+    assert ((lam_g - lam_c).abs()[big] <= 1e-4 * lam_c[big]).all()
+    rec = Vh_g.mH @ (lam_g.to(C128)[:, :, None] * Vh_g)
+    assert (rec - G).abs().max() <= 1e-12 * G.abs().max()
+    gram = Vh_g @ Vh_g.mH
+    d = gram.diagonal(dim1=1, dim2=2).real
+    assert (((d - 1).abs() <= 1e-10) | (d.abs() <= 1e-300)).all()
+    off = gram - torch.diag_embed(gram.diagonal(dim1=1, dim2=2))
+    assert off.abs().max() <= 1e-10
+    assert (lam_g[:, rk:] <= 1e-12 * top).all()
+
+
+@pytest.mark.gpu
+def test_eigh_psd_blocked_factorisation_structured(cuda_prims):
+    """Cases that defeat a factorisation without pivoting unless null pivots are handled: zero rows in the middle, a tiny
+    leading diagonal coupled to a large one, exactly repeated rows, the identity."""
+    n = 96
+    Gs = []
+    G = torch.zeros((n, n), dtype=C128); Gs.append(G)                                   # zero matrix
+    Gs.append(torch.eye(n, dtype=C128) * 2.5)                                            # identity
+    v = rnd((1, n, 3), C128, 5)[0]; v[10:20] = 0; Gs.append(v @ v.mH)                    # rank 3, zero rows inside
+    w = rnd((1, n, n), C128, 6)[0]; w[0] *= 1e-7; Gs.append(w @ w.mH)                    # tiny leading diagonal, coupled
+    u = rnd((1, n, 40), C128, 7)[0]; u[50:] = u[:46]; Gs.append(u @ u.mH)                # repeated rows (rank 40)
+    G = torch.stack([0.5 * (g + g.mH) for g in Gs])
+    lam_g, Vh_g = cuda_prims.eigh_psd(G.cuda(), rank_revealing=2)
+    lam_g, Vh_g = lam_g.cpu(), Vh_g.cpu()
+    for b in range(G.shape[0]):
+        lam_c = torch.linalg.eigvalsh(G[b]).flip(-1).clamp_min(0.0)
+        top = max(float(lam_c.max()), 1e-300)
+        assert (lam_g[b] - lam_c).abs().max() <= 1e-11 * top, b
+        rec = Vh_g[b].mH @ (lam_g[b].to(C128)[:, None] * Vh_g[b])
+        assert (rec - G[b]).abs().max() <= 1e-11 * max(float(G[b].abs().max()), 1e-300), b
+
+
+@pytest.mark.gpu
 def test_eigh_psd_rank_revealing_zero_and_identity(cuda_prims):
     G = torch.zeros((3, 16, 16), dtype=C128)
     G[1] = torch.eye(16, dtype=C128) * 3.0

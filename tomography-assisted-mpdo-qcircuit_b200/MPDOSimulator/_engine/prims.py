@@ -179,7 +179,9 @@ class CudaPrims:
     def eigh_psd(self, G, tol=1e-15, sweeps=30, rank_revealing=False, rel=1e-15):
         """Hermitian PSD G [B,n,n] (complex128) -> lam [B,n] descending, Vh [B,n,n] with G = Vh^h diag(lam) Vh.
         rank_revealing: pivoted-Cholesky preconditioned route (mpdo_eigh_psd); directions below rel * max diag come
-        back as lam = 0 with zero rows of Vh. Otherwise the complete basis from Jacobi on [G | I]."""
+        back as lam = 0 with zero rows of Vh. rank_revealing = 2: the blocked factorisation without pivoting where the
+        shape allows (Gram matrices of fp32 data; see include/mpdo_b200.h). Otherwise the complete basis from Jacobi
+        on [G | I]."""
         G = G.contiguous()
         Bn, n, _ = G.shape
         assert G.dtype == torch.complex128
@@ -190,7 +192,7 @@ class CudaPrims:
         Vh = torch.empty((Bn, n, n), dtype=torch.complex128, device=dev)
         tol = max(tol, 4.4e-16 * (n ** 0.5))
         _lib.check(self.lib.mpdo_eigh_psd(Bn, n, self._ptr(G), self._ptr(scratch), self._ptr(lam), self._ptr(Vh),
-                                          1 if rank_revealing else 0, float(rel), float(tol), int(sweeps),
+                                          int(rank_revealing), float(rel), float(tol), int(sweeps),
                                           self._stream()), 'mpdo_eigh_psd')
         return lam, Vh
 

@@ -647,6 +647,209 @@ __global__ void __launch_bounds__(CC_THREADS) chol_cluster_kernel(CholArgs p) {
   if (c == 0 && tid == 0) p.info[4LL * bidx] = rank;
 }
 
+// ---- medium matrices, no pivoting: blocked right-looking Cholesky on a 16-CTA cluster --------------------------------
+// The pivoted kernels above pay one cluster barrier (and two dependent DSMEM round trips) for every pivot: 3.3 us per
+// step, 0.64 / 0.96 ms at n = 192 / 256 - a third of the device time of an MPDO layer at chi = 64, all of it on the
+// sequential chain of the truncation sweep. Where the factor only preconditions the Jacobi eigen-solver the pivot order
+// buys nothing on this workload: on the Gram matrices of the sweeps (tools/data/grams_sel.npz, n = 148 / 194 / 256)
+// one-sided Jacobi takes the same number of sweeps (8 / 7 / 9), the same number of rotations to within 1 % and reaches
+// the same relative eigenvalue accuracy (1e-13) on the unpivoted factor as on the pivoted one (model: tools/jacobi_model
+// .py). Without pivoting the factorisation blocks: the rows are dealt to the ceil(n / 16) CTAs of a cluster in panels
+// of R = 16 (CTA c keeps rows 16 c .. 16 c + 15 of the lower triangle in shared memory), and a panel costs two cluster
+// barriers whatever its width:
+//   1. the owner factors its R x R diagonal block and inverts the factor;                           cluster barrier
+//   2. every CTA below multiplies its block of the panel by the inverse (L_qp = A_qp L_pp^-h);      cluster barrier
+//   3. every CTA below pulls the panel blocks L_rp of the CTAs between the owner and itself through distributed shared
+//      memory and updates its slab, A_qr -= L_qp L_rp^h.
+// Rank safety without pivoting: a diagonal that has dropped to rel * max diag(G) is a null direction; for a positive
+// semidefinite matrix its whole column of the Schur complement is then zero to the same level (|S_ik|^2 <= S_ii S_kk),
+// so the column is skipped (zero column of L, the rows of Y stay compact) instead of being divided by.
+// Outputs as chol_kernel (Y row k = conj(column k of L) over the accepted columns, info[0] = their number) except that
+// the columns follow the initial diagonal order; no left inverse (p.X must be null; Y zeroed by the caller).
+constexpr int CU_CTAS = 16;
+constexpr int CU_RMAX = 16;
+constexpr int CU_THREADS = 256;
+constexpr int CU_LB = CU_RMAX + 1;   // leading dimension of the staged R x R blocks
+
+__global__ void __launch_bounds__(CU_THREADS) chol_blocked_kernel(CholArgs p) {
+  extern __shared__ double2 usm[];
+  __shared__ double sDiag[CU_CTAS * CU_RMAX];   // diagonal of G
+  __shared__ int sPerm[CU_CTAS * CU_RMAX];      // position -> original index, by decreasing diagonal
+  __shared__ int sAcc[CU_RMAX + 1];  // owner of the current panel: compact index of each column or -1; [R] = count
+  __shared__ int sAccL[CU_RMAX + 1]; // local copy of the current owner's header
+  cg::cluster_group cl = cg::this_cluster();
+  const int n = p.n, R = p.R, bidx = blockIdx.y;
+  const int c = (int)cl.block_rank();
+  const int C = (n + R - 1) / R;     // panels = CTAs that own rows
+  const int tid = threadIdx.x;
+  const int ti = tid >> 4, tj = tid & 15;
+  const int row0 = c * R;
+  const int rows = max(0, min(R, n - row0));
+  const int ld = n + 1;
+  const double2* G = p.G + (long long)bidx * n * n;
+  double2* Y = p.Y + (long long)bidx * n * n;
+  double2* A = usm;                                   // [R][ld]: A[r * ld + j] = entry (row0 + r, j), j <= row0 + r
+  double2* Lall = A + (size_t)R * ld;                 // [C - 1][R][CU_LB]: panel blocks of the CTAs above
+  double2* Dinv = Lall + (size_t)(C > 1 ? C - 1 : 1) * R * CU_LB;   // [R][CU_LB]: inverse of the diagonal factor
+
+  // Symmetric permutation by decreasing diagonal first ("diagonal pivoting at the start", every CTA computes the same
+  // order): a direction whose diagonal is tiny from the outset is then met last, after everything it is coupled to has
+  // been eliminated. Skipping a tiny pivot EARLY would drop couplings of up to sqrt(rel) relative size
+  // (|S_ik|^2 <= S_ii S_kk is all positive semidefiniteness gives; measured 3e-8 on a complex128 circuit).
+  for (int i = tid; i < n; i += CU_THREADS) sDiag[i] = G[(long long)i * n + i].x;
+  __syncthreads();
+  for (int i = tid; i < n; i += CU_THREADS) {
+    const double di = sDiag[i];
+    int before = 0;
+    for (int j = 0; j < n; ++j) {
+      const double dj = sDiag[j];
+      before += (dj > di || (dj == di && j < i)) ? 1 : 0;
+    }
+    sPerm[before] = i;
+  }
+  __syncthreads();
+  for (int idx = tid; idx < rows * n; idx += CU_THREADS) {
+    const int r = idx / n, j = idx - r * n;
+    if (j <= row0 + r) A[(size_t)r * ld + j] = G[(long long)sPerm[row0 + r] * n + sPerm[j]];
+  }
+  const double thresh = p.rel * sDiag[sPerm[0]];
+
+  int base = 0;   // accepted columns before the current panel (the same number in every CTA)
+  for (int pp = 0; pp < C; ++pp) {
+    const int c0 = pp * R;
+    const int pr = min(R, n - c0);
+    if (c == pp) {
+      // ---- 1. diagonal block: unpivoted Cholesky with null-pivot skipping, thread (ti, tj) owns entry (ti, tj)
+      int cnt = 0;
+      for (int k = 0; k < pr; ++k) {
+        __syncthreads();
+        const double d = A[(size_t)k * ld + c0 + k].x;
+        const bool ok = d > thresh && d > 0.0;
+        const double s = ok ? sqrt(d) : 0.0;
+        if (tj == k && ti > k && ti < pr) {          // column k below the diagonal (the diagonal entry itself is
+          double2 v = A[(size_t)ti * ld + c0 + k];   // still being read as `d` by slower warps: written below)
+          if (!ok) {
+            v = make_double2(0.0, 0.0);
+          } else {
+            const double inv = 1.0 / s;
+            v.x *= inv;
+            v.y *= inv;
+          }
+          A[(size_t)ti * ld + c0 + k] = v;
+        }
+        if (tid == 0) sAcc[k] = ok ? cnt : -1;
+        cnt += ok ? 1 : 0;
+        __syncthreads();
+        if (ti == k && tj == k) A[(size_t)k * ld + c0 + k] = make_double2(s, 0.0);
+        if (ok && tj > k && tj <= ti && ti < pr) {   // trailing part of the block: A[i][j] -= L[i][k] conj(L[j][k])
+          const double2 a = A[(size_t)ti * ld + c0 + k], b = A[(size_t)tj * ld + c0 + k];
+          double2 v = A[(size_t)ti * ld + c0 + tj];
+          v.x -= a.x * b.x + a.y * b.y;
+          v.y -= a.y * b.x - a.x * b.y;
+          A[(size_t)ti * ld + c0 + tj] = v;
+        }
+      }
+      if (tid == 0) sAcc[R] = cnt;
+      __syncthreads();
+      // inverse of the factor, X = L_pp^-1 (lower triangular; zero rows / columns for skipped pivots): thread per
+      // column, forward substitution down the column
+      if (tid < pr) {
+        const int j = tid;
+        const double ljj = A[(size_t)j * ld + c0 + j].x;
+        for (int i = 0; i < j; ++i) Dinv[i * CU_LB + j] = make_double2(0.0, 0.0);
+        Dinv[j * CU_LB + j] = make_double2(ljj > 0.0 ? 1.0 / ljj : 0.0, 0.0);
+        for (int i = j + 1; i < pr; ++i) {
+          const double lii = A[(size_t)i * ld + c0 + i].x;
+          double ar = 0.0, ai = 0.0;
+          for (int m = j; m < i; ++m) {
+            const double2 a = A[(size_t)i * ld + c0 + m], x = Dinv[m * CU_LB + j];
+            ar += a.x * x.x - a.y * x.y;
+            ai += a.x * x.y + a.y * x.x;
+          }
+          const double inv = (lii > 0.0 && ljj > 0.0) ? -1.0 / lii : 0.0;
+          Dinv[i * CU_LB + j] = make_double2(ar * inv, ai * inv);
+        }
+      }
+      // rows of Y for the accepted columns of the diagonal block
+      if (ti < pr && tj <= ti) {
+        const int a = sAcc[tj];
+        if (a >= 0) {
+          const double2 v = A[(size_t)ti * ld + c0 + tj];
+          Y[(long long)(base + a) * n + sPerm[row0 + ti]] = make_double2(v.x, -v.y);
+        }
+      }
+    }
+    cl.sync();   // the owner's header and inverse are visible cluster-wide
+    if (tid <= R) sAccL[tid] = cl.map_shared_rank(sAcc, pp)[tid];
+    if (c > pp && rows > 0) {
+      // ---- 2. own block of the panel: L_qp[i][k] = sum_{m <= k} A_qp[i][m] conj(X[k][m])
+      double2* Dl = Lall;   // staged copy of the owner's inverse (Lall is free until step 3)
+      if (ti < pr && tj < pr) Dl[ti * CU_LB + tj] = cl.map_shared_rank(Dinv, pp)[ti * CU_LB + tj];
+      __syncthreads();
+      double2 val = make_double2(0.0, 0.0);
+      if (ti < rows && tj < pr) {
+        for (int m = 0; m <= tj; ++m) {
+          const double2 a = A[(size_t)ti * ld + c0 + m], x = Dl[tj * CU_LB + m];
+          val.x += a.x * x.x + a.y * x.y;
+          val.y += a.y * x.x - a.x * x.y;
+        }
+      }
+      __syncthreads();
+      if (ti < rows && tj < pr) {
+        A[(size_t)ti * ld + c0 + tj] = val;
+        const int a = sAccL[tj];
+        if (a >= 0) Y[(long long)(base + a) * n + sPerm[row0 + ti]] = make_double2(val.x, -val.y);
+      }
+    } else {
+      __syncthreads();   // sAccL visible to the whole CTA
+    }
+    cl.sync();   // every block of the panel is final
+    if (c > pp && rows > 0) {
+      // ---- 3. trailing update of the slab: pull L_rp of the CTAs pp < r < c, then A_qr -= L_qp L_rp^h for pp < r <= c
+      const int nb = c - pp - 1;
+      for (int idx = tid; idx < nb * R * pr; idx += CU_THREADS) {
+        const int b = idx / (R * pr), rem = idx - b * (R * pr);
+        const int j = rem / pr, m = rem - j * pr;
+        Lall[((size_t)b * R + j) * CU_LB + m] = cl.map_shared_rank(A, pp + 1 + b)[(size_t)j * ld + c0 + m];
+      }
+      __syncthreads();
+      if (ti < rows) {
+        double2 lq[CU_RMAX];
+#pragma unroll
+        for (int m = 0; m < CU_RMAX; ++m) lq[m] = m < pr ? A[(size_t)ti * ld + c0 + m] : make_double2(0.0, 0.0);
+        for (int r = pp + 1; r <= c; ++r) {
+          const int rr = min(R, n - r * R);            // rows of CTA r = columns of this block
+          if (tj >= rr || (r == c && tj > ti)) continue;
+          const double2* lr = r == c ? A + (size_t)tj * ld + c0 : Lall + ((size_t)(r - pp - 1) * R + tj) * CU_LB;
+          double sr = 0.0, si = 0.0;
+#pragma unroll
+          for (int m = 0; m < CU_RMAX; ++m) {
+            if (m < pr) {
+              const double2 b = lr[m];
+              sr += lq[m].x * b.x + lq[m].y * b.y;
+              si += lq[m].y * b.x - lq[m].x * b.y;
+            }
+          }
+          double2 v = A[(size_t)ti * ld + r * R + tj];
+          v.x -= sr;
+          v.y -= si;
+          A[(size_t)ti * ld + r * R + tj] = v;
+        }
+      }
+    }
+    base += sAccL[R];
+    __syncthreads();   // sAccL is rewritten after the next cluster barrier; the slab update is complete
+  }
+  cl.sync();   // nobody leaves while a neighbour may still read its slab
+  if (c == 0 && tid == 0) p.info[4LL * bidx] = base;
+}
+
+// panels of CU_RMAX rows, one CTA each: the cluster has ceil(n / 16) CTAs
+static size_t chol_blocked_smem(int n) {
+  const int R = CU_RMAX, C = (n + R - 1) / R;
+  return ((size_t)R * (n + 1) + (size_t)(C > 1 ? C - 1 : 1) * R * CU_LB + (size_t)R * CU_LB) * sizeof(double2);
+}
+
 static size_t chol_cluster_smem(int n, bool inverse) {
   return ((size_t)n * CC_LD + (size_t)n + CC_R + (inverse ? (size_t)CC_R * n : 0)) * sizeof(double2);
 }
@@ -1008,6 +1211,92 @@ __global__ void gather_rank_kernel(int batch, const int* __restrict__ info, int3
 }
 }  // namespace mpdo
 
+namespace mpdo {
+// Launch of the blocked unpivoted factorisation (factor only). Returns 1 when the shape / device cannot run it (the
+// caller takes the pivoted kernels), 0 on success with *rcOut = 0, or 0 with a CUDA error code in *rcOut.
+static int chol_blocked_launch(int batch, int n, const void* G, void* Y, int* info, double rel, cudaStream_t st,
+                               int* rcOut) {
+  *rcOut = 0;
+  static const bool pivoted = getenv("MPDO_CHOL_PIVOTED") != nullptr;   // A/B knob: always the pivoted kernels
+  static const int minN = getenv("MPDO_CHOL_BLOCKED_MIN") ? atoi(getenv("MPDO_CHOL_BLOCKED_MIN")) : 17;   // A/B knob
+  if (pivoted || n < minN || n > CU_CTAS * CU_RMAX || batch > 65535) return 1;
+  const int C = (n + CU_RMAX - 1) / CU_RMAX;   // CTAs per matrix = cluster size
+  static std::mutex mu;
+  static int usable[CU_CTAS + 1];   // per cluster size: 0 unknown, 1 usable, -1 not
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    static bool attrs = false;
+    if (!attrs) {
+      attrs = true;
+      if (cudaFuncSetAttribute(chol_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)chol_blocked_smem(CU_CTAS * CU_RMAX)) != cudaSuccess ||
+          cudaFuncSetAttribute(chol_blocked_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+        cudaGetLastError();
+        for (int i = 0; i <= CU_CTAS; ++i) usable[i] = -1;
+      }
+    }
+    if (usable[C] == 0) {
+      usable[C] = -1;
+      cudaLaunchConfig_t q = {};
+      q.gridDim = dim3(C, 1);
+      q.blockDim = dim3(CU_THREADS);
+      q.dynamicSmemBytes = chol_blocked_smem(C * CU_RMAX);
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = C;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int nClusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nClusters, chol_blocked_kernel, &q) == cudaSuccess && nClusters >= 1)
+        usable[C] = 1;
+      else
+        cudaGetLastError();
+    }
+    if (usable[C] != 1) return 1;
+  }
+  cudaError_t e = cudaMemsetAsync(info, 0, sizeof(int) * 4 * (size_t)batch, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(Y, 0, sizeof(double2) * (size_t)batch * n * n, st);
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "chol memset: %s", cudaGetErrorString(e));
+    *rcOut = (int)e;
+    return 0;
+  }
+  CholArgs a;
+  a.n = n;
+  a.R = CU_RMAX;
+  a.rel = rel;
+  a.G = (const double2*)G;
+  a.Y = (double2*)Y;
+  a.X = nullptr;
+  a.slots = nullptr;
+  a.info = info;
+  a.cluster = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(C, batch);
+  cfg.blockDim = dim3(CU_THREADS);
+  cfg.dynamicSmemBytes = chol_blocked_smem(n);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = C;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  TimedLaunch timed(2, 8.0 * batch * ((double)n * n * n / 3.0), 16.0 * batch * (double)n * n * 2.0, st);
+  e = cudaLaunchKernelEx(&cfg, chol_blocked_kernel, a);
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "chol_blocked_kernel: %s", cudaGetErrorString(e));
+    *rcOut = (int)e;
+    return 0;
+  }
+  *rcOut = check_launch("chol_blocked_kernel");
+  return 0;
+}
+}  // namespace mpdo
+
 extern "C" int mpdo_eigh_psd(int batch, int n, const void* G, void* scratch, double* lam, void* Vh, int precondition,
                              double rel, double tol, int maxSweeps, void* stream) {
   using namespace mpdo;
@@ -1020,7 +1309,10 @@ extern "C" int mpdo_eigh_psd(int batch, int n, const void* G, void* scratch, dou
   if (precondition && !off && n > 1) {
     const EighLayout l = eigh_layout(batch, n, true, (n + 7) / 8);
     int rc = 0;
-    if (chol_launch(batch, n, G, base + l.y, nullptr, base + l.slots, l.info - l.slots, (int*)(base + l.info), rel, st,
+    // precondition = 2: the factor only preconditions the Jacobi phase and the caller's data are fp32 - the blocked
+    // factorisation without pivoting (see chol_blocked_kernel); shapes it cannot take fall through to the pivoted kernels
+    if ((precondition == 2 && chol_blocked_launch(batch, n, G, base + l.y, (int*)(base + l.info), rel, st, &rc) == 0) ||
+        chol_launch(batch, n, G, base + l.y, nullptr, base + l.slots, l.info - l.slots, (int*)(base + l.info), rel, st,
                     &rc) == 0) {
       if (rc) return rc;
       int32_t* work = (int32_t*)(base + l.work);

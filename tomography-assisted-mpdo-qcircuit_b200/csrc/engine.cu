@@ -337,7 +337,7 @@ static int eigh(Ctx& c, const Tn& G, double** lam, Tn* Vh) {
     *lam = c.ar.reals((long long)B * n);
     *Vh = c.ar.alloc(MPDO_C128, {(long long)B, (long long)n, (long long)n});
     ARENA_OK(c);
-    return mpdo_eigh_psd(B, n, G.p, scratch, *lam, Vh->p, c.precondition ? 1 : 0, c.chol_rel,
+    return mpdo_eigh_psd(B, n, G.p, scratch, *lam, Vh->p, c.precondition ? (c.f32 ? 2 : 1) : 0, c.chol_rel,
                          std::max(c.jtol, 4.4e-16 * sqrt((double)n)), 30, c.st);
   }
   Tn none;

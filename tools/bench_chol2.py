@@ -23,4 +23,6 @@ for n in (32, 64, 80, 96, 128, 160, 192, 224, 256):
     G = graded(n, 0.93)
     t_inv = timeit(lambda: p.chol_psd(G))
     t_eig = timeit(lambda: p.eigh_psd(G, 1e-10, rank_revealing=True))
-    print('n=%4d  chol+inverse %.3f ms   eigh (chol + jacobi + finalize) %.3f ms' % (n, t_inv, t_eig), flush=True)
+    t_eig2 = timeit(lambda: p.eigh_psd(G, 1e-10, rank_revealing=2))
+    print('n=%4d  chol+inverse %.3f ms   eigh (pivoted chol + jacobi + finalize) %.3f ms   eigh (blocked chol, no pivoting) %.3f ms'
+          % (n, t_inv, t_eig, t_eig2), flush=True)
