@@ -588,9 +588,9 @@ def b200_arm(args):
                     'accumulated Gram matrices whose own ceiling is the fp64 pipe (largest_launch.frac_of_fp64_pipe). Device time is split between this kernel and the two latency-bound '
                     'factorisation kernels (see factorisation_kernels).',
         }
-        # DRAM traffic of the largest contraction launch (the kappa Gram matrix) from the committed `ncu --set full`
-        # capture, next to its algorithmic bytes; and the same launch against the fp64 pipe it actually runs on
-        tr = os.path.join(ROOT, 'profiles', 'r1_traffic.json')
+        # DRAM traffic of the largest contraction launch of a layer (the environment step of a wide site) from the
+        # committed `ncu --set full` capture, next to its algorithmic bytes
+        tr = os.path.join(ROOT, 'profiles', 'r2_traffic.json')
         if os.path.exists(tr):
             t = json.load(open(tr))
             roof['traffic'] = t['dram_read_bytes'] + t['dram_write_bytes']
@@ -622,22 +622,25 @@ def b200_arm(args):
         roof['dominant_by_device_time'] = ('factorisation kernels (see factorisation_kernels): after the work reductions '
                                            'of round 2 the contractions are a few per cent of the layer')
         dominant = {
-            'jacobi': {'kernel': 'jacobi_kernel / jacobi_persistent_kernel (one-sided Jacobi on fp64 rows in shared memory)',
+            'jacobi': {'kernel': 'jacobi_cluster_kernel / jacobi_kernel (one-sided Jacobi on the rows of the Cholesky factor, fp64, '
+                                 'cluster-resident in shared memory for 32 < n <= 256)',
                        'launches': t_jacobi['launches'], 'kernel_seconds': jt,
                        'avg_launch_us': 1e6 * jt / max(t_jacobi['launches'], 1),
                        'share_of_timed_device_seconds': jt / (ct + jt + ht),
                        'algorithmic_TFLOP/s': t_jacobi['flops'] / jt / 1e12,
                        'frac': t_jacobi['flops'] / jt / 1e12 / fp64_peak, 'peak': fp64_peak,
                        'flops_convention': 'SURVEY 8d SVD count 4 (6 m n^2 + 20 n^3) per decomposition'},
-            'cholesky': {'kernel': 'chol_kernel (rank-revealing pivoted Cholesky, rows of L resident in shared memory)',
+            'cholesky': {'kernel': 'chol_blocked_kernel (blocked, no pivoting: preconditioner of the eigen-solver) + '
+                                   'chol_cluster_kernel / chol_small_kernel (rank-revealing pivoted, with the left inverse: '
+                                   'factors of the bond environments)',
                          'launches': t_chol['launches'], 'kernel_seconds': ht,
                          'avg_launch_us': 1e6 * ht / max(t_chol['launches'], 1),
                          'share_of_timed_device_seconds': ht / (ct + jt + ht),
                          'algorithmic_TFLOP/s': t_chol['flops'] / ht / 1e12,
                          'frac': t_chol['flops'] / ht / 1e12 / fp64_peak, 'peak': fp64_peak,
                          'flops_convention': '8 n^3 / 3 for the factor + the same for the left inverse'},
-            'bound': 'latency: one device-wide barrier per tournament round / pivot step on 1-64 SMs per matrix '
-                     '(ncu: profiles/)',
+            'bound': 'latency: one cluster barrier per tournament round / pivot step / half panel on the 4-16 SMs of a '
+                     'matrix (ncu: profiles/r2_ncu_kernels.md)',
             'note': 'kernel seconds are summed over concurrent streams, so they can exceed the wall time of the step',
         }
         cpu = None

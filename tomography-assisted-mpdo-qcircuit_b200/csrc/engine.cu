@@ -889,7 +889,10 @@ extern "C" int mpdo_kappa_truncate(int dtype, int B, int l, int a, int r, const 
   std::atomic<int>& skip = topkSkip[slot];
   std::atomic<int>& stalls = topkStalls[slot];
   static const bool noTopk = getenv("MPDO_NO_TOPK") != nullptr;   // A/B knob: always the full decomposition
-  bool tryTopk = !noTopk && max_err < 0 && a >= 64 && a >= 8 * k;
+  // (for one or a few circuits the full decomposition of a Gram matrix below order 256 is a fraction of a millisecond
+  // and the iteration cannot beat it; a probe that lands in a steady-state step only costs - measured 15-95 ms with
+  // its first-time scratch shapes)
+  bool tryTopk = !noTopk && max_err < 0 && a >= 64 && a >= 8 * k && (a >= 256 || B >= 16);
   bool claimed = false;
   if (tryTopk && stalls.load(std::memory_order_relaxed) > 0) {   // this signature stalled before: paused / one prober
     int cur = skip.load(std::memory_order_relaxed);
