@@ -47,11 +47,18 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// One-sided Jacobi converges quadratically: a sweep in which the largest relative inner product met is mu leaves
+// nothing above ~mu^2 behind (measured on the Gram matrices of the sweeps, tools/jacobi_model.py: 9.2e-5 -> 2.5e-8 ->
+// 1e-10). A rotation reports bit 1 when |<x,y>|^2 > JACOBI_QUAD tol |x|^2 |y|^2, i.e. mu > 0.3 sqrt(tol); a sweep
+// without such a rotation has converged to tol and the sweep that would only confirm it is not run.
+constexpr double JACOBI_QUAD = 0.09;
+
 // Rotate rows x, y (shared memory) so that their first m entries become orthogonal; G lanes cooperate on one
 // pair (32/G pairs per warp). The kernel is instruction-issue bound (ncu: ~2 IPC, half of the issue slots busy, 6
 // warps per scheduler each spending ~440 instructions per rotation, most of them reduction / scalar / index
 // overhead rather than row arithmetic), so short rows share that overhead between several pairs of one warp.
-// Every lane of the warp runs the shuffles; `active` only predicates the memory traffic. Returns 1 if rotated.
+// Every lane of the warp runs the shuffles; `active` only predicates the memory traffic. Returns 0 if the pair was left
+// alone, 1 after a rotation by a small angle, 3 after a large one (JACOBI_QUAD).
 template <int G>
 __device__ __forceinline__ int rotate_pair(double2* __restrict__ x, double2* __restrict__ y, bool active, int m,
                                            int mt, double tol,
@@ -101,7 +108,7 @@ __device__ __forceinline__ int rotate_pair(double2* __restrict__ x, double2* __r
     x[k] = xn;
     y[k] = yn;
   }
-  return 1;
+  return (g2 > JACOBI_QUAD * tol * ab) ? 3 : 1;
 }
 
 // Round-robin partner tables: `np` players (even), round r in [0, np-1), pair q in [0, np/2). Division free.
@@ -531,7 +538,7 @@ __device__ __forceinline__ int rotate_regs(double2 (&x)[E], double2* __restrict_
     x[e] = xn;
     if (k < mt) yrow[k] = yn;
   }
-  return 1;
+  return (g2 > JACOBI_QUAD * tol * ab) ? 3 : 1;
 }
 
 constexpr int JC_MAXC = 16;   // CTAs per cluster (non-portable above 8)
@@ -674,15 +681,17 @@ __global__ void __launch_bounds__(256, 1) jacobi_cluster_kernel(JacobiArgs p, do
         }
       }
       if (round == nbp - 1) {   // end of the sweep: tell every CTA of the cluster whether this one rotated
-        const int any = __syncthreads_or(rot);
-        if (threadIdx.x < C) cl.map_shared_rank(flags, threadIdx.x)[q] = any;
+        const int anyRot = __syncthreads_or(rot & 1), anyBig = __syncthreads_or(rot & 2);
+        if (threadIdx.x < C) cl.map_shared_rank(flags, threadIdx.x)[q] = (anyRot ? 1 : 0) | (anyBig ? 2 : 0);
       }
       cl.sync();   // parked / pushed rows (and the sweep flags) are visible cluster-wide; perm is updated
     }
     int anyAll = 0;
     for (int c = 0; c < C; ++c) anyAll |= flags[c];
     if (q == 0 && threadIdx.x == 0) cnt[sw] = anyAll;
-    if (!anyAll) break;   // the same flags in every CTA
+    static_assert(JACOBI_QUAD > 0, "");
+    if (!(anyAll & 1) || !(anyAll & 2)) break;   // no rotation, or small ones only (quadratic convergence): the same
+                                                 // flags in every CTA
   }
 
   if (act) {
