@@ -87,6 +87,17 @@ def rdm_checks(circ, n):
     return {'rdm_hermiticity': herm, 'rdm_min_eig_over_trace': (ev.min() / ev.sum()).item()}
 
 
+def release_device_memory():
+    """Circuits are nn.Modules with reference cycles: the state and operand tensors of the previous configuration
+    stay allocated until the cyclic collector runs (cfg4 left ~90 GB behind and cfg5 then ran out of memory)."""
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    from MPDOSimulator._engine import lib as _lib
+    _lib.load().mpdo_trim_pools()
+
+
 def run_single(tag, n, depth, dtype, chi, kappa, noise, chip, entangler, prefix_ghz=False, trunc_after_1q=True,
                files=None, readout=None):
     dev = 'cuda:0'
@@ -201,6 +212,7 @@ def main():
                 run_batched('warmup', 16, 3, 64, 4, 8, 8)
             elif cfg == 5:
                 run_single('warmup', 12, 3, C64, 256, 8, 'idealNoise', 'medium', 'cz')
+        release_device_memory()
         torch.cuda.reset_peak_memory_stats()
         if cfg == 1:
             r = run_single('cfg1', 10, ds(10), C64, 32, 4, 'idealNoise', 'medium', 'cz', prefix_ghz=True)

@@ -17,7 +17,7 @@ from torch.linalg import LinAlgError  # noqa: F401  (part of the reference's err
 
 from . import _engine
 from ._node import DenseNode, replicate_nodes
-from ._engine.strands import adopt, hand_over, run_strands
+from ._engine.strands import adopt, hand_over, memory_guard, run_strands
 from .AbstractCircuit import QuantumCircuit
 from .NoiseChannel import NoiseChannel
 from .QuantumGates.AbstractGate import QuantumGate
@@ -307,9 +307,11 @@ class TensorCircuit(QuantumCircuit):
             name = layer.name.lower()
             if 'truncate' in name:
                 self._run_segment(state, segment)
+                memory_guard(self.device, [s.data for s in state])      # large states only (cfg5), see strands.py
                 if checkConnectivity(state):
                     truncateLayer(state, chi=self.chi, kappa=self.kappa, max_truncation_err=self.max_truncation_err,
                                   noisy=not self.ideal)
+                    memory_guard(self.device, [s.data for s in state])
             elif 'barrier' in name:
                 pass
             else:

@@ -41,7 +41,11 @@ def bondTruncate(_qubits: List[DenseNode], max_singular_values: Optional[int] = 
     if _use_env_form(_qubits, max_singular_values, max_truncation_err):
         eng = _engine_of(_qubits)
         Ts = [q.data for q in _qubits]
-        eng.bond_truncate_env(Ts, max_singular_values)
+
+        def publish(idx, tensor):       # sites are final one by one, right to left: release what they replace at once
+            _qubits[idx].data = tensor
+
+        eng.bond_truncate_env(Ts, max_singular_values, publish=publish)
         for q, t in zip(_qubits, Ts):
             q.data = t
         return None

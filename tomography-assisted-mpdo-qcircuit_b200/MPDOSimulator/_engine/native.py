@@ -9,6 +9,7 @@ import torch
 
 from . import lib as _lib
 from .steps import Engine
+from .strands import BIG_STATE_BYTES, memory_guard, state_bytes
 
 _DT = {torch.complex64: _lib.MPDO_C64, torch.complex128: _lib.MPDO_C128}
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_int, C.c_int64, C.c_void_p)
@@ -23,7 +24,6 @@ def _p(t):
 
 
 _CUDA_OOM = 2   # cudaErrorMemoryAllocation
-
 
 class NativeEngine(Engine):
     def __init__(self, prims, dtype, npass=None):
@@ -71,16 +71,20 @@ class NativeEngine(Engine):
         disc = sv[:, k:].clamp_min(0).sqrt() if self.npass == 1 else sv[:, k:]
         return Tl_n, Tr_n, disc
 
-    def bond_truncate_env(self, Ts, chi):
+    def bond_truncate_env(self, Ts, chi, publish=None):
         """steps.Engine.bond_truncate_env as two kinds of library calls: mpdo_env_sweep (environment chain on the
         current stream, the factorisations of all bonds on the library's side streams) and one mpdo_bond_env_step per
-        bond, right to left. No host synchronisation."""
+        bond, right to left. No host synchronisation (except on states of more than 1 GB, see memory_guard).
+        `publish(idx, tensor)` hands every finished site to the caller at once, so that the tensor it replaces and the
+        C.T product of that bond are released while the sweep goes on (not a layer's worth of them at the end)."""
         n = len(Ts)
         if n < 2:
             return []
         Ts[:] = [t.contiguous() for t in Ts]
         Bn = Ts[0].shape[0]
         dev = Ts[0].device
+        big = state_bytes(Ts) >= BIG_STATE_BYTES
+        memory_guard(dev, Ts, need=state_bytes(Ts))
         if Ts[0].shape[1] != 1:
             raise ValueError('the first site must have a trivial left bond')
         ls = (C.c_int * n)(*[t.shape[1] for t in Ts])
@@ -104,11 +108,18 @@ class NativeEngine(Engine):
             self._call('mpdo_bond_env_step', self.lib.mpdo_bond_env_step, self.dt, Bn, l, a, r0, _p(M0), rw,
                        None if W is None else _p(W), _p(Cis[idx]), k, _p(T_n), _p(W_n), _p(sv), _stream())
             Ts[idx], W = T_n, W_n
+            Ms[idx] = Cis[idx] = M0 = None
+            if publish is not None:
+                publish(idx, T_n)
             disc.append(sv[:, k:].clamp_min(0).sqrt())
+            if big and (n - idx) % 8 == 0:
+                memory_guard(dev, Ts)
         T0 = Ts[0]
         out = torch.empty(tuple(T0.shape[:4]) + (W.shape[2],), dtype=T0.dtype, device=dev)
         self.p.contract(T0, (1, 3, 1), W, (1, 1, 1), out, (1, 3, 1))
         Ts[0] = out
+        if publish is not None:
+            publish(0, out)
         return disc
 
     def kappa_truncate(self, T, kappa, max_err=None):

@@ -417,7 +417,7 @@ class Engine:
         p.contract(Ci.permute(0, 2, 1), (1, 1, 1), UL.permute(0, 2, 1), (1, 1, 1), W_n, (1, 1, 1), conjA=True, conjB=True)
         return T_n, W_n, disc
 
-    def bond_truncate_env(self, Ts, chi):
+    def bond_truncate_env(self, Ts, chi, publish=None):
         """bondTruncate (QR sweep + chi sweep, TNNOptimizer.py:72-134) for complex64 states with a fixed chi, in place
         on the list of site tensors. The left-to-right pass only chains the environments E_i (contractions); their
         factorisations are independent of one another; the right-to-left pass is the only sequential chain of
@@ -442,11 +442,16 @@ class Engine:
         for idx in range(n - 1, 0, -1):
             M0, Ci = factors[idx]
             Ts[idx], W, d = self.bond_env_step(M0, W, Ci, chi)
+            factors[idx] = M0 = Ci = None
+            if publish is not None:     # the caller takes the finished site at once (and drops the one it replaces)
+                publish(idx, Ts[idx])
             disc.append(d)
         T0 = Ts[0]
         out = self._empty(tuple(T0.shape[:4]) + (W.shape[2],), T0)
         p.contract(T0, (1, 3, 1), W, (1, 1, 1), out, (1, 3, 1))
         Ts[0] = out
+        if publish is not None:
+            publish(0, out)
         return disc
 
     # ------------------------------------------------------------------------------------------

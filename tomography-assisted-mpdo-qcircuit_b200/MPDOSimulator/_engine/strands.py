@@ -112,3 +112,29 @@ def hand_over(tensor, device):
     if tensor.is_cuda:
         tensor.record_stream(torch.cuda.current_stream(torch.device(device)))
     return tensor
+
+
+BIG_STATE_BYTES = 1 << 30
+_TOTAL = {}
+
+
+def state_bytes(Ts):
+    return sum(t.numel() * t.element_size() for t in Ts)
+
+
+def memory_guard(dev, Ts, need=0):
+    """Bounds how far the host runs ahead of the device on LARGE states (chi = 256, ~100 sites: tens of GB). Nothing
+    in a truncation sweep synchronises, and tensors that crossed streams (strands) are only returned to the caching
+    allocator when the device has passed their last use - with a layer that takes seconds on the device, a layer's
+    worth of dead site tensors stays allocated beside the live ones (cfg5 at full size ran out of 178 GB). When the
+    state is large and the allocator holds more than a third of the device, wait for the device: the dead tensors
+    become reusable, and the host had nothing to do but wait anyway. States below 1 GB (every latency-bound
+    workload) never get here."""
+    if not Ts or not Ts[0].is_cuda or state_bytes(Ts) < BIG_STATE_BYTES:
+        return
+    dev = torch.device(dev)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _TOTAL:
+        _TOTAL[idx] = torch.cuda.get_device_properties(idx).total_memory
+    if torch.cuda.memory_allocated(idx) + need > _TOTAL[idx] // 3:
+        torch.cuda.synchronize(idx)

@@ -1,5 +1,5 @@
 """Dev helper (GPU): one launch of each kernel that matters after round 2, at its steady-state cfg2 / cfg5 size, for
-`ncu --set full -k regex:"tc_apply|chol_small|chol_cluster|jacobi_cluster|jacobi_kernel|contract_kernel"`.
+`ncu --set full -k regex:"tc_apply|chol_small|chol_cluster|chol_blocked|jacobi_cluster|jacobi_kernel|contract_kernel"`.
 
   tc_apply_kernel<128,3> / <256,2>          : complex64 apply 65536 x 256 x 256, default and widest column tile
   chol_cluster_kernel + jacobi_cluster_kernel : preconditioned eigen-decomposition of graded 192 x 192 and 256 x 256
@@ -36,6 +36,8 @@ for n, decay in ((192, 0.93), (256, 0.94)):
     G = graded(n, decay)
     for _ in range(2):
         p.eigh_psd(G, 1e-10, rank_revealing=True)
+    for _ in range(2):                   # the route of complex64 states: blocked Cholesky without pivoting in front
+        p.eigh_psd(G, 1e-10, rank_revealing=2)
     torch.cuda.synchronize()
 G64 = graded(64, 0.8)
 for _ in range(2):
