@@ -103,8 +103,11 @@ def test_absorb_1q(cuda_prims, dt, K, Bg):
     assert (g.cpu() - c).abs().max() <= (1e-5 if dt == C64 else 1e-13) * c.abs().max().item()
 
 
-@pytest.mark.parametrize('n,Bn', [(1, 2), (2, 2), (5, 3), (16, 2), (64, 2), (65, 1), (100, 2), (200, 1)])
+@pytest.mark.parametrize('n,Bn', [(1, 2), (2, 2), (5, 3), (16, 2), (64, 2), (65, 1), (100, 2), (200, 1), (300, 1),
+                                  (330, 2), (500, 1)])
 def test_eigh_psd(cuda_prims, n, Bn):
+    """Complete basis from Jacobi on [G | I] (the complex128 route). n > 256: rows of 2n entries, block pairs held in
+    registers (jacobi_persistent_cols_kernel); (330, 2) is two matrices sharing the device."""
     A = rnd((Bn, n, n + 3), C128, 11)
     G = A @ A.mH
     lam_g, Vh_g = cuda_prims.eigh_psd(G.cuda())

@@ -562,10 +562,15 @@ __global__ void __launch_bounds__(JR_THREADS, 1) jacobi_persistent_cols_kernel(J
     part[buf][warp][myIdx] = v[0];                                                                   \
     __syncthreads();                                                                                 \
     /* totals (lane l: sum number l mod V), the same order of additions in every warp */             \
-    double tot = 0;                                                                                  \
+    double tot;                                                                                      \
     {                                                                                                \
       const int idx = lane & (V - 1);                                                                \
-      _Pragma("unroll") for (int w = 0; w < JR_WARPS; ++w) tot += part[buf][w][idx];                 \
+      double tw[JR_WARPS];                                                                           \
+      _Pragma("unroll") for (int w = 0; w < JR_WARPS; ++w) tw[w] = part[buf][w][idx];                \
+      _Pragma("unroll") for (int h = JR_WARPS / 2; h >= 1; h >>= 1) {  /* fixed tree: 4 levels */    \
+        _Pragma("unroll") for (int w = 0; w < h; ++w) tw[w] += tw[w + h];                            \
+      }                                                                                              \
+      tot = tw[0];                                                                                   \
     }                                                                                                \
     buf ^= 1;                                                                                        \
     /* lane q (mod BR) works out the rotation of pair q */                                           \

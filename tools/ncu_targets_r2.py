@@ -52,4 +52,9 @@ for _ in range(2):
     p.contract(T, (1, 1, 1), T.permute(0, 2, 1), (1, 1, 1), Gm, (1, 1, 1), conjB=True, acc64=True, hermitian=True)
     p.contract(E, (1, 1, 1), T, (1, 1, 1), X, (1, 1, 1))
 torch.cuda.synchronize()
+# long rows: block pairs in registers, sliced by columns (jacobi_persistent_cols_kernel), order 1024 as in cfg5
+G1k = graded(1024, 0.975)
+for _ in range(2):
+    p.eigh_psd(G1k, 1e-10, rank_revealing=True)
+torch.cuda.synchronize()
 print('done')
