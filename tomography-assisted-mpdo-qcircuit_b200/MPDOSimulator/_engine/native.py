@@ -97,6 +97,12 @@ class NativeEngine(Engine):
         mp = (C.c_void_p * n)(*[None if m is None else m.data_ptr() for m in Ms])
         self._call('mpdo_env_sweep', self.lib.mpdo_env_sweep, self.dt, Bn, n, ls, as_, rs, tp, cip, mp, _stream())
         W, disc = None, []
+        # squared singular values of all bonds in one buffer: the discarded ones are clamped and rooted by ONE pair of
+        # launches after the sweep instead of one per bond inside the sequential chain
+        sv_off = [0] * (n + 1)
+        for idx in range(1, n):
+            sv_off[idx + 1] = sv_off[idx] + Bn * Ts[idx].shape[1]
+        sv_all = torch.empty((max(sv_off[n], 1),), dtype=torch.float64, device=dev)
         for idx in range(n - 1, 0, -1):
             M0 = Ms[idx]
             _, l, _, a, r0 = M0.shape
@@ -104,16 +110,17 @@ class NativeEngine(Engine):
             k = l if chi is None else min(int(chi), l)
             T_n = torch.empty((Bn, k, 2, a, rw), dtype=M0.dtype, device=dev)
             W_n = torch.empty((Bn, l, k), dtype=M0.dtype, device=dev)
-            sv = torch.empty((Bn, l), dtype=torch.float64, device=dev)
+            sv = sv_all[sv_off[idx]:sv_off[idx + 1]].view(Bn, l)
             self._call('mpdo_bond_env_step', self.lib.mpdo_bond_env_step, self.dt, Bn, l, a, r0, _p(M0), rw,
                        None if W is None else _p(W), _p(Cis[idx]), k, _p(T_n), _p(W_n), _p(sv), _stream())
             Ts[idx], W = T_n, W_n
             Ms[idx] = Cis[idx] = M0 = None
             if publish is not None:
                 publish(idx, T_n)
-            disc.append(sv[:, k:].clamp_min(0).sqrt())
+            disc.append(sv[:, k:])
             if big and (n - idx) % 8 == 0:
                 memory_guard(dev, Ts)
+        sv_all.clamp_min_(0).sqrt_()      # (the kept values are rooted too; only the discarded ones are handed out)
         T0 = Ts[0]
         out = torch.empty(tuple(T0.shape[:4]) + (W.shape[2],), dtype=T0.dtype, device=dev)
         self.p.contract(T0, (1, 3, 1), W, (1, 1, 1), out, (1, 3, 1))
