@@ -61,3 +61,34 @@ def test_env_sweep_complex64_inside_fp32_floor():
     exact.evolve()
     e1, e2 = rel(r1.to(C128), exact.cal_dm()), rel(r2.to(C128), exact.cal_dm())
     assert e2 < max(2e-5, 3 * e1), (e1, e2)
+
+
+def test_env_sweep_hands_sites_over_one_by_one():
+    """`publish` receives every site exactly once, right to left with site 0 last, and what it receives is what the
+    list holds afterwards (the caller drops the tensor a site replaces while the sweep goes on: large states)."""
+    oc = _circuit(6, 3, 4, 2, C128, seed=13)
+    from MPDOSimulator._engine.steps import Engine
+    E, Ts = run_engine(oc, CpuPrims(), C128, npass=1)
+    cz = torch.diag(torch.tensor([1, 1, 1, -1], dtype=C128)).reshape(1, 2, 2, 2, 2, 1)
+    for q in range(0, 5, 2):
+        Ts[q], Ts[q + 1] = E.split_2q(Ts[q], Ts[q + 1], cz)
+    A, B = [t.clone() for t in Ts], [t.clone() for t in Ts]
+    seen = []
+    d1 = E.bond_truncate_env(A, 3)
+    d2 = E.bond_truncate_env(B, 3, publish=lambda idx, t: seen.append((idx, t)))
+    assert [i for i, _ in seen] == [5, 4, 3, 2, 1, 0]
+    for idx, t in seen:
+        assert t is B[idx]
+    for x, y in zip(A, B):
+        assert torch.equal(x, y)
+    for x, y in zip(d1, d2):
+        assert torch.equal(x, y)
+
+
+def test_memory_guard_is_a_no_op_off_device_and_on_small_states():
+    from MPDOSimulator._engine import strands
+    small = [torch.zeros(4, dtype=C64)]
+    assert strands.state_bytes(small) == 32
+    strands.memory_guard('cpu', small)           # host tensors: returns without touching CUDA
+    strands.memory_guard('cuda:0', [])           # empty state
+    assert strands.BIG_STATE_BYTES == 1 << 30

@@ -311,173 +311,6 @@ __global__ void __launch_bounds__(1024) jacobi_persistent_kernel(JacobiArgs p, d
   }
 }
 
-// Persistent kernel for LONG rows (mt >= 512: the Cholesky factors / [G | I] rows of the chi = 128 / 256 configurations).
-// With one warp per row pair a CTA of b = 6..8 row blocks has 6-8 warps on its SM, each walking 16 KB rows alone: a
-// round of n = 1024 took 27 us (measured: 36 ms per decomposition, 46 % of the device time of a chi = 256 layer).
-// Here W warps share one row pair (W b warps per CTA, up to 32): each takes every W-th group of 32 entries, the four
-// partial sums of a pair meet in shared memory (one extra CTA barrier per step), every warp evaluates the same
-// rotation from the same sums (bitwise identical, summed in a fixed order) and updates its own entries. Staging and
-// write-back use the whole CTA. Same tournament, barrier protocol and convergence flags as jacobi_persistent_kernel;
-// the sweep that would only confirm convergence is not run (JACOBI_QUAD).
-constexpr int JW_MAXB = 8, JW_MAXW = 16;
-
-__global__ void __launch_bounds__(1024) jacobi_persistent_wide_kernel(JacobiArgs p, double2* __restrict__ Yall, int W) {
-  extern __shared__ double2 smem[];                 // [2b][mt]
-  __shared__ double part[JW_MAXB][JW_MAXW][4];      // partial (|x|^2, |y|^2, Re g, Im g) of every pair slot
-  const int bidx = blockIdx.y;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int slot = warp / W, sub = warp - slot * W;  // pair slot 0..b-1, share of the row 0..W-1
-  const int k0 = sub * 32 + lane, kstride = 32 * W;
-  const int b = p.b, mt = p.mt, m = p.m;
-  const int nthreads = blockDim.x;
-  int* cnt = p.cnt + (long long)bidx * WORK_INTS;
-  const double amax = *reinterpret_cast<const double*>(cnt + 32);
-  const double floor2 = fmax(1e-290, 1e-48 * amax * amax);
-  unsigned* bar = reinterpret_cast<unsigned*>(cnt + 34);
-  int* errflag = cnt + 35;
-  unsigned phase = 0;
-  double2* Y = Yall + (long long)bidx * p.batchStride;
-  const int nrows = p.rank ? min(p.n, p.rank[(long long)bidx * p.rankStride]) : p.n;
-  if (nrows < 2) return;   // uniform over the CTAs of this matrix: nobody reaches a barrier
-  const int nbp = (((nrows + b - 1) / b) + 1) & ~1;
-  const unsigned ncta = min((unsigned)(nbp / 2), gridDim.x);
-  if (blockIdx.x >= ncta) return;
-  const int half = b / 2;   // b is even (launch)
-  const double tol = p.tol;
-
-  // one rotation step of the CTA: pair slot `slot` works on rows x, y (shared memory); returns the rotate_pair flags
-  auto step_pair = [&](double2* __restrict__ x, double2* __restrict__ y, bool active) -> int {
-    double a = 0, bq = 0, gr = 0, gi = 0;
-    if (active) {
-#pragma unroll 4
-      for (int k = k0; k < m; k += kstride) {
-        const double2 u = x[k], v = y[k];
-        a = fma(u.x, u.x, fma(u.y, u.y, a));
-        bq = fma(v.x, v.x, fma(v.y, v.y, bq));
-        gr = fma(u.x, v.x, fma(u.y, v.y, gr));
-        gi = fma(u.y, v.x, fma(-u.x, v.y, gi));
-      }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      a += __shfl_xor_sync(0xffffffffu, a, o);
-      bq += __shfl_xor_sync(0xffffffffu, bq, o);
-      gr += __shfl_xor_sync(0xffffffffu, gr, o);
-      gi += __shfl_xor_sync(0xffffffffu, gi, o);
-    }
-    if (lane == 0 && slot < b) {
-      double* q = part[slot][sub];
-      q[0] = a;
-      q[1] = bq;
-      q[2] = gr;
-      q[3] = gi;
-    }
-    __syncthreads();
-    int flag = 0;
-    if (active) {
-      a = bq = gr = gi = 0;
-      for (int w = 0; w < W; ++w) {   // the same order in every warp of the pair: identical rotation
-        const double* q = part[slot][w];
-        a += q[0];
-        bq += q[1];
-        gr += q[2];
-        gi += q[3];
-      }
-      const double g2 = gr * gr + gi * gi;
-      const double ab = a * bq;
-      if ((ab > floor2) && (g2 > tol * tol * ab)) {
-        const double d = 0.5 * (bq - a);
-        const double ad = fabs(d);
-        const double h = sqrt(fma(d, d, g2));
-        const double ru = rsqrt(2.0 * h * (h + ad));
-        const double c = (h + ad) * ru;
-        const double sg = d >= 0 ? ru : -ru;
-        const double sr = sg * gr, si = sg * gi;
-#pragma unroll 4
-        for (int k = k0; k < mt; k += kstride) {
-          const double2 u = x[k], v = y[k];
-          double2 xn, yn;
-          xn.x = c * u.x - (sr * v.x - si * v.y);
-          xn.y = c * u.y - (sr * v.y + si * v.x);
-          yn.x = (sr * u.x + si * u.y) + c * v.x;
-          yn.y = (sr * u.y - si * u.x) + c * v.y;
-          x[k] = xn;
-          y[k] = yn;
-        }
-        flag = (g2 > JACOBI_QUAD * tol * ab) ? 3 : 1;
-      }
-    }
-    __syncthreads();   // rows and partial sums are reused by the next step
-    return flag;
-  };
-
-  for (int sw = 0; sw < p.maxSweeps; ++sw) {
-    int rotSweep = 0;
-    for (int round = 0; round < nbp - 1; ++round) {
-      int rot = 0;
-      for (int pairIdx = blockIdx.x; pairIdx < nbp / 2; pairIdx += ncta) {
-        int I, J;
-        rr_pair(nbp, round, pairIdx, I, J);
-        // stage with the whole CTA, four rows in flight per thread (L2 reads: other SMs wrote these rows last round)
-        for (int v0 = 0; v0 < 2 * b; v0 += 4) {
-          for (int k = threadIdx.x; k < mt; k += nthreads) {
-            double2 t[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int v = v0 + j;
-              const int row = (v < b) ? I * b + v : J * b + (v - b);
-              t[j] = (v < 2 * b && row < nrows) ? __ldcg(Y + (long long)row * p.ld + k) : make_double2(0.0, 0.0);
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (v0 + j < 2 * b) smem[(size_t)(v0 + j) * mt + k] = t[j];
-          }
-        }
-        __syncthreads();
-        if (round == 0) {   // once per sweep: the pairs inside each of the two blocks
-          for (int step = 0; step < b - 1; ++step) {
-            const int blk = slot >= half ? 1 : 0;
-            int a0, a1;
-            rr_pair(b, step, slot - blk * half, a0, a1);
-            const int first = (blk ? J : I) * b;
-            const bool active = slot < b && first + a0 < nrows && first + a1 < nrows;
-            rot |= step_pair(smem + (size_t)(blk * b + a0) * mt, smem + (size_t)(blk * b + a1) * mt, active);
-          }
-        }
-        for (int step = 0; step < b; ++step) {
-          int a1 = slot + step;
-          if (a1 >= b) a1 -= b;
-          const bool active = slot < b && I * b + slot < nrows && J * b + a1 < nrows;
-          rot |= step_pair(smem + (size_t)slot * mt, smem + (size_t)(b + a1) * mt, active);
-        }
-        for (int v = 0; v < 2 * b; ++v) {   // write back
-          const int row = (v < b) ? I * b + v : J * b + (v - b);
-          if (row < nrows) {
-            double2* dst = Y + (long long)row * p.ld;
-            const double2* src = smem + (size_t)v * mt;
-            for (int k = threadIdx.x; k < mt; k += nthreads) dst[k] = src[k];
-          }
-        }
-        __syncthreads();   // the staging area is reused by the next pair of this CTA
-      }
-      if (ncta > 1) {
-        if ((rot & 2) && lane == 0 && sub == 0) atomicAdd(&cnt[sw], 1);
-        matrix_barrier(bar, ncta, phase, errflag);
-      } else {
-        rotSweep |= rot;
-        __threadfence_block();
-      }
-    }
-    if (ncta > 1) {
-      if (*((volatile int*)&cnt[sw]) == 0 || *((volatile int*)errflag)) break;
-    } else {
-      const int any = __syncthreads_or(rotSweep & 2);
-      if (threadIdx.x == 0) cnt[sw] = any;
-      if (!any) break;
-    }
-  }
-}
-
 // Persistent kernel for LONG rows with the block pair held in REGISTERS, sliced by columns (mt in 257..1024 for blocks of
 // 4 rows, 257..512 for blocks of 8). The kernels above move every row pair through shared memory six times per rotation
 // (ncu: they are bound by the 128 B/clk of shared memory, ~1.6 us per step of eight 8 KB row pairs), and with one warp
@@ -1443,92 +1276,6 @@ int jacobi_rows_ranked(int batch, int n, int m, int mt, int ld, long long batchS
           }
         }
         if (ok) return 0;   // first launch refused: the older kernels below
-      }
-    }
-  }
-  {
-    // long rows, few matrices: several warps per row pair (jacobi_persistent_wide_kernel). MPDO_JACOBI_NOWIDE is the
-    // A/B knob.
-    static const bool noWide = getenv("MPDO_JACOBI_WIDE") == nullptr;   // measured SLOWER than one warp per pair (shared-memory
-    // bandwidth, not warps, bounds these kernels: n = 512 16.4 -> 24.3 ms, n = 1024 59 -> 75 ms): opt-in, kept for A/B
-    static std::mutex wideMu;
-    static int wideOk = 0, wideSms = 0;   // 0 unknown, 1 usable, -1 not
-    if (trace && !noWide && mt >= 512) fprintf(stderr, "[mpdo] jacobi wide candidate (state %d)\n", wideOk);
-    if (!noWide && mt >= 512) {
-      const long long rowB = (long long)mt * sizeof(double2);
-      int bw = (int)((smemMax - 6144) / (2 * rowB));   // 4 KB of static shared memory (partial sums) + margin
-      if (bw > JW_MAXB) bw = JW_MAXB;
-      bw &= ~1;
-      const int Ww = bw >= 2 ? (32 / bw > JW_MAXW ? JW_MAXW : 32 / bw) : 0;
-      if (bw >= 2 && n > 2 * bw) {
-        {
-          std::lock_guard<std::mutex> lk(wideMu);
-          if (wideOk == 0) {
-            int dev = 0, coopAttr = 0;
-            wideOk = -1;
-            if (cudaGetDevice(&dev) == cudaSuccess &&
-                cudaDeviceGetAttribute(&coopAttr, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coopAttr &&
-                cudaDeviceGetAttribute(&wideSms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess &&
-                cudaFuncSetAttribute(jacobi_persistent_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     smemMax - 6144) == cudaSuccess)
-              wideOk = 1;
-            else
-              cudaGetLastError();
-          }
-        }
-        const int nbw = (n + bw - 1) / bw;
-        const int nbpw = (nbw + 1) & ~1;
-        const size_t smemW = (size_t)(2 * bw) * rowB;
-        const unsigned thr = 32u * (unsigned)(Ww * bw);
-        int perSm = 0;
-        if (wideOk == 1 && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, jacobi_persistent_wide_kernel, (int)thr,
-                                                                         smemW) != cudaSuccess) {
-          cudaGetLastError();
-          perSm = 0;
-        }
-        const long long capacity = (long long)perSm * wideSms;
-        if (wideOk == 1 && capacity >= nbpw / 2) {
-          int chunk = (int)(capacity / (nbpw / 2));
-          if (chunk > batch) chunk = batch;
-          JacobiArgs a;
-          a.n = n;
-          a.m = m;
-          a.mt = mt;
-          a.ld = ld;
-          a.batchStride = batchStride;
-          a.b = bw;
-          a.nbp = nbpw;
-          a.round = 0;
-          a.sweep = 0;
-          a.maxSweeps = maxSweeps;
-          a.loop = 0;
-          a.tol = tol;
-          a.rankStride = rankStride;
-          bool ok = true;
-          for (int b0 = 0; b0 < batch && ok; b0 += chunk) {
-            const int nbat = batch - b0 < chunk ? batch - b0 : chunk;
-            a.cnt = work + (long long)b0 * WORK_INTS;
-            a.rank = rank ? rank + (long long)b0 * rankStride : nullptr;
-            double2* Yc = (double2*)Y + (long long)b0 * batchStride;
-            int Wa = Ww;
-            void* args[] = {(void*)&a, (void*)&Yc, (void*)&Wa};
-            TimedLaunch timed(1, 4.0 * nbat * (6.0 * m * (double)n * n + 20.0 * (double)n * n * n),
-                              32.0 * nbat * (double)n * m, st);
-            cudaError_t e = cudaLaunchCooperativeKernel((const void*)jacobi_persistent_wide_kernel,
-                                                        dim3((unsigned)(nbpw / 2), nbat), dim3(thr), args, smemW, st);
-            if (e == cudaSuccess) {
-              ++g_launches;
-            } else {
-              cudaGetLastError();
-              ok = false;
-              if (b0 > 0) {
-                snprintf(g_err, sizeof(g_err), "jacobi_persistent_wide (chunk %d): %s", b0, cudaGetErrorString(e));
-                return (int)e;
-              }
-            }
-          }
-          if (ok) return 0;   // first launch refused: the older kernels below
-        }
       }
     }
   }
