@@ -30,7 +30,7 @@ def graded(n, lo, B=1):
 print('knobs', {k: v for k, v in os.environ.items() if k.startswith('MPDO_')})
 for n, B in ((300, 1), (384, 1), (512, 1), (768, 1), (1024, 1), (512, 4)):
     G, lam_true = graded(n, 1e-12, B)
-    for rr, tol in ((True, 1e-10), (False, 1e-15)):
+    for rr, tol in ((int(os.environ.get('RR', '1')), 1e-10), (False, 1e-15)):
         if not rr and n > 512 and os.environ.get('SKIP_BIG_CLASSIC'):
             continue
         lam, Vh = p.eigh_psd(G, tol, rank_revealing=rr)
@@ -43,4 +43,4 @@ for n, B in ((300, 1), (384, 1), (512, 1), (768, 1), (1024, 1), (512, 4)):
         rel = ((lam[0, :k] - lam_true[:k]).abs() / lam_true[:k]).max().item()
         t = timeit(lambda: p.eigh_psd(G, tol, rank_revealing=rr))
         print('n=%4d B=%d %-14s rank %4d  recon %.1e  orth %.1e  lam abs %.1e rel %.1e   %8.3f ms' %
-              (n, B, 'chol+jacobi' if rr else 'classic [G|I]', k, err, orth, lerr, rel, t), flush=True)
+              (n, B, ('chol+jacobi rr=%d' % rr) if rr else 'classic [G|I]', k, err, orth, lerr, rel, t), flush=True)
