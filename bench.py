@@ -293,6 +293,14 @@ def cfg4_leg(dev, rank, world, barrier):
     gc.collect()
     gc.freeze()                               # see b200_arm: no full collection inside a timed region
     barrier()
+
+    def allocator():                          # cudaMalloc / cudaFree calls and out-of-memory retries of torch's allocator
+        ms = torch.cuda.memory_stats(dev)     # so far: a leg that needed them explains a slower leg (they synchronise)
+        return {'device_alloc': int(ms.get('num_device_alloc', 0)), 'device_free': int(ms.get('num_device_free', 0)),
+                'alloc_retries': int(ms.get('num_alloc_retries', 0)),
+                'reserved_GB': round(ms.get('reserved_bytes.all.current', 0) / 2 ** 30, 2)}
+
+    alloc_log = {'after_rehearsal': allocator()}
     # device-resident leg: circuit objects (gate operands) built before the clock starts
     c = build(ang_host)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -302,6 +310,7 @@ def cfg4_leg(dev, rank, world, barrier):
     e1.record()
     barrier()
     secs = e0.elapsed_time(e1) * 1e-3
+    alloc_log['after_value_leg'] = allocator()
     # end-to-end leg: angles start in pinned host memory, circuits are built, evolved, read out, gathered and the
     # table lands in host memory, all inside the timed region; gate operands uploaded are counted
     orig_dev = Simulator.TensorCircuit._dev
@@ -321,11 +330,13 @@ def cfg4_leg(dev, rank, world, barrier):
     barrier()
     Simulator.TensorCircuit._dev = orig_dev
     e2e_secs = f0.elapsed_time(f1) * 1e-3
+    alloc_log['after_e2e_leg'] = allocator()
     finite = bool(torch.isfinite(host_table).all())
     same = float((table - table2).abs().max())
     return {'secs': secs, 'e2e_secs': e2e_secs, 'circuits_per_rank': len(ids), 'total': total, 'updates': updates,
             'h2d': copied[0], 'd2h': host_table.numel() * 8, 'finite': finite, 'repeat_diff': same,
-            'trace_like_p0_first': float(host_table[0, -1]), 'peak_mem_GB': torch.cuda.max_memory_allocated() / 2 ** 30}
+            'trace_like_p0_first': float(host_table[0, -1]), 'peak_mem_GB': torch.cuda.max_memory_allocated() / 2 ** 30,
+            'allocator': alloc_log}
 
 
 def b200_arm(args):
@@ -688,7 +699,7 @@ def b200_arm(args):
                            'warmup': 'one untimed rehearsal of the identical batch',
                            'l2': 'the batched site tensors (537 MB per layer sweep) exceed L2'},
                 'checks': {'readout_finite': cfg4['finite'], 'repeat_max_abs_diff': cfg4['repeat_diff'],
-                           'peak_mem_GB': cfg4['peak_mem_GB']},
+                           'peak_mem_GB': cfg4['peak_mem_GB'], 'allocator': cfg4['allocator']},
             }
             if world == 1 and not args.no_cpu_baseline:
                 secs4, cores4 = cfg4_cpu_sample()
